@@ -1,0 +1,374 @@
+// fdgs_api.cu -- C-ABI entry points (include/fdgs.h) and scratch-buffer carving.
+//
+// Host-side orchestration of one forward / backward pass; replaces
+// CudaRasterizer::Rasterizer::forward / backward / markVisible
+// (reference: rasterizer_impl.cu:199-364, :368-496, :142-154) and the GeometryState /
+// ImageState / BinningState chunk carving (rasterizer_impl.cu:156-195, rasterizer_impl.h:21-73).
+#include <string.h>
+#include <string>
+#include "../../include/fdgs.h"
+#include "fdgs_internal.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define FDGS_CUDA(expr, what)                                                                         \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess)                                                                        \
+            return fail(FDGS_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(_e));            \
+    } while (0)
+
+#define FDGS_STAGE(expr, what)                                                                        \
+    do {                                                                                              \
+        FDGS_CUDA(expr, what);                                                                        \
+        if (debug) {                                                                                  \
+            cudaError_t _s = cudaStreamSynchronize(stream);                                           \
+            if (_s != cudaSuccess)                                                                    \
+                return fail(FDGS_ERR_CUDA, std::string(what) + " (debug sync): " + cudaGetErrorString(_s)); \
+        }                                                                                             \
+    } while (0)
+
+// bump allocator over one chunk; every sub-array 128-byte aligned (like the reference's obtain())
+struct Carver {
+    char* base;
+    size_t off;
+    explicit Carver(char* b) : base(b), off(0) {}
+    template <typename T>
+    T* take(size_t count) {
+        off = (off + 127) & ~(size_t)127;
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+    size_t total() const { return off + 128; }
+};
+
+struct GeomState {
+    float* depths;
+    float* means2D;
+    float* conic_opacity;
+    float* rgb;
+    float* cov3D;
+    uint8_t* clamped;
+    uint32_t* tiles_touched;
+    uint32_t* point_offsets;
+    char* scan_temp;
+    size_t scan_bytes;
+    size_t bytes;
+    static GeomState carve(char* base, int P) {
+        GeomState g;
+        Carver c(base);
+        const size_t p = (size_t)(P > 0 ? P : 0);
+        g.cov3D = c.take<float>(6 * p);   // first: 128-byte aligned [P,6] view for covs3D_com
+        g.depths = c.take<float>(p);
+        g.means2D = c.take<float>(2 * p);
+        g.conic_opacity = c.take<float>(4 * p);
+        g.rgb = c.take<float>(3 * p);
+        g.clamped = c.take<uint8_t>(p);
+        g.tiles_touched = c.take<uint32_t>(p);
+        g.point_offsets = c.take<uint32_t>(p);
+        g.scan_bytes = fdgs::scan_temp_bytes(P > 0 ? P : 1);
+        g.scan_temp = c.take<char>(g.scan_bytes);
+        g.bytes = c.total();
+        return g;
+    }
+};
+
+struct ImageState {
+    float* final_T;
+    uint32_t* n_contrib;
+    uint2* ranges;
+    size_t bytes;
+    static ImageState carve(char* base, int W, int H) {
+        ImageState s;
+        Carver c(base);
+        const size_t N = (size_t)W * H;
+        const size_t tiles = (size_t)((W + fdgs::TILE_X - 1) / fdgs::TILE_X) * ((H + fdgs::TILE_Y - 1) / fdgs::TILE_Y);
+        s.final_T = c.take<float>(N);
+        s.n_contrib = c.take<uint32_t>(N);
+        s.ranges = c.take<uint2>(tiles);
+        s.bytes = c.total();
+        return s;
+    }
+};
+
+struct BinningState {
+    fdgs::InstRec* recs;
+    uint32_t* point_list;
+    uint64_t* keys_sorted;
+    uint64_t* keys_unsorted;
+    uint32_t* vals_unsorted;
+    char* sort_temp;
+    size_t sort_bytes;
+    size_t bytes;
+    static BinningState carve(char* base, int R) {
+        BinningState b;
+        Carver c(base);
+        const size_t r = (size_t)(R > 0 ? R : 0);
+        b.recs = c.take<fdgs::InstRec>(r);
+        b.point_list = c.take<uint32_t>(r);
+        b.keys_sorted = c.take<uint64_t>(r);
+        b.keys_unsorted = c.take<uint64_t>(r);
+        b.vals_unsorted = c.take<uint32_t>(r);
+        b.sort_bytes = fdgs::sort_temp_bytes(R > 0 ? R : 1);
+        b.sort_temp = c.take<char>(b.sort_bytes);
+        b.bytes = c.total();
+        return b;
+    }
+};
+
+char* align128(char* p) {
+    return reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(p) + 127) & ~(uintptr_t)127);
+}
+
+void sh_staging(const float* shs, int M, int* bulk_ok, int* stride_floats) {
+    *bulk_ok = 0;
+    *stride_floats = 0;
+    if (!shs || M <= 0) return;
+    if ((M % 4) != 0 || (reinterpret_cast<uintptr_t>(shs) % 16) != 0) return;
+    int q = (3 * M) / 4 + 1;   // 16-byte units incl. padding
+    if ((q & 1) == 0) ++q;     // odd stride in 16-byte units -> conflict-free LDS.128 / STS.128
+    if ((size_t)q * 16 * 128 > 200 * 1024) return;
+    *bulk_ok = 1;
+    *stride_floats = q * 4;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fdgs_version(void) { return FDGS_VERSION; }
+
+const char* fdgs_last_error(void) { return g_last_error.c_str(); }
+
+size_t fdgs_geom_bytes(int P) { return GeomState::carve(nullptr, P).bytes + 128; }
+size_t fdgs_image_bytes(int width, int height) { return ImageState::carve(nullptr, width, height).bytes + 128; }
+size_t fdgs_binning_bytes(int num_rendered, int, int) { return BinningState::carve(nullptr, num_rendered).bytes + 128; }
+
+int fdgs_forward(const fdgs_forward_args* a, fdgs_alloc_fn geom_alloc, void* geom_ctx, fdgs_alloc_fn binning_alloc,
+                 void* binning_ctx, fdgs_alloc_fn image_alloc, void* image_ctx, void* stream_v,
+                 fdgs_forward_result* res) {
+    g_last_error.clear();
+    if (!a || !res || !geom_alloc || !binning_alloc || !image_alloc) return fail(FDGS_ERR_INVALID_ARG, "null argument");
+    memset(res, 0, sizeof(*res));
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+    const bool debug = a->debug != 0;
+    const int P = a->P, W = a->width, H = a->height;
+    if (P < 0 || W <= 0 || H <= 0) return fail(FDGS_ERR_INVALID_ARG, "bad P / width / height");
+    if (P > 0) {
+        if (!a->means3D || !a->opacities || !a->viewmatrix || !a->projmatrix || !a->cam_pos || !a->background)
+            return fail(FDGS_ERR_INVALID_ARG, "means3D/opacities/viewmatrix/projmatrix/cam_pos/background must be set");
+        if (!a->out_means3D || !a->out_color || !a->out_flow || !a->out_depth || !a->out_T || !a->radii)
+            return fail(FDGS_ERR_INVALID_ARG, "output pointers must be set");
+        if (!a->cov3D_precomp) {
+            if (!a->scales || !a->rotations) return fail(FDGS_ERR_INVALID_ARG, "scales/rotations or cov3D_precomp required");
+            if (a->rot_4d && (!a->rotations_r || !a->scales_t || !a->ts))
+                return fail(FDGS_ERR_INVALID_ARG, "rot_4d needs rotations_r, scales_t and ts");
+            if (!a->rot_4d && a->gaussian_dim == 4 && (!a->scales_t || !a->ts))
+                return fail(FDGS_ERR_INVALID_ARG, "gaussian_dim 4 needs scales_t and ts");
+        }
+        if (!a->colors_precomp) {
+            // reference: rasterizer_impl.cu:255-258 (NUM_CHANNELS is 3 here, so SHs are required)
+            if (!a->shs) return fail(FDGS_ERR_INVALID_ARG, "either shs or colors_precomp required");
+            const bool sh3d = a->gaussian_dim == 3 || a->force_sh_3d;
+            int need = (a->D + 1) * (a->D + 1);
+            if (!sh3d && a->D > 2 && a->D_t > 0) need = 16 * (a->D_t + 1);
+            if (a->D < 0 || a->D > 3 || a->D_t < 0 || a->D_t > 2 || a->M < need)
+                return fail(FDGS_ERR_INVALID_ARG, "SH degree / coefficient count mismatch");
+            if (!sh3d && !a->ts) return fail(FDGS_ERR_INVALID_ARG, "4D SH needs ts");
+        }
+    }
+    const int grid_x = (W + fdgs::TILE_X - 1) / fdgs::TILE_X, grid_y = (H + fdgs::TILE_Y - 1) / fdgs::TILE_Y;
+    const size_t N = (size_t)W * H;
+
+    // scratch: geometry + image
+    const size_t geom_bytes = fdgs_geom_bytes(P);
+    char* geom_raw = geom_alloc(geom_ctx, geom_bytes);
+    if (!geom_raw) return fail(FDGS_ERR_ALLOC, "geometry buffer allocation failed");
+    GeomState geom = GeomState::carve(align128(geom_raw), P);
+    const size_t img_bytes = fdgs_image_bytes(W, H);
+    char* img_raw = image_alloc(image_ctx, img_bytes);
+    if (!img_raw) return fail(FDGS_ERR_ALLOC, "image buffer allocation failed");
+    ImageState img = ImageState::carve(align128(img_raw), W, H);
+    res->geom_buffer = geom_raw;
+    res->geom_bytes = geom_bytes;
+    res->image_buffer = img_raw;
+    res->image_bytes = img_bytes;
+    res->cov3D = geom.cov3D;
+
+    int num_rendered = 0;
+    if (P > 0) {
+        fdgs::PreprocessFwdParams pp;
+        memset(&pp, 0, sizeof(pp));
+        pp.P = P; pp.D = a->D; pp.D_t = a->D_t; pp.M = a->M;
+        pp.means3D = a->means3D; pp.ts = a->ts; pp.scales = a->scales; pp.scales_t = a->scales_t;
+        pp.scale_modifier = a->scale_modifier; pp.rotations = a->rotations; pp.rotations_r = a->rotations_r;
+        pp.opacities = a->opacities; pp.shs = a->shs; pp.cov3D_precomp = a->cov3D_precomp;
+        pp.prefilter_var = a->prefilter_var; pp.colors_precomp = a->colors_precomp;
+        pp.viewmatrix = a->viewmatrix; pp.projmatrix = a->projmatrix; pp.cam_pos = a->cam_pos;
+        pp.timestamp = a->timestamp; pp.time_duration = a->time_duration;
+        pp.rot_4d = a->rot_4d; pp.gaussian_dim = a->gaussian_dim; pp.force_sh_3d = a->force_sh_3d;
+        pp.W = W; pp.H = H; pp.tan_fovx = a->tan_fovx; pp.tan_fovy = a->tan_fovy;
+        // reference: rasterizer_impl.cu:235-236
+        pp.focal_y = H / (2.0f * a->tan_fovy);
+        pp.focal_x = W / (2.0f * a->tan_fovx);
+        pp.grid_x = grid_x; pp.grid_y = grid_y; pp.prefiltered = a->prefiltered;
+        sh_staging(a->colors_precomp ? nullptr : a->shs, a->M, &pp.sh_bulk_ok, &pp.sh_row_stride_floats);
+        pp.out_means3D = a->out_means3D; pp.radii = a->radii; pp.means2D = geom.means2D; pp.depths = geom.depths;
+        pp.cov3D = geom.cov3D; pp.rgb = geom.rgb; pp.conic_opacity = geom.conic_opacity; pp.clamped = geom.clamped;
+        pp.tiles_touched = geom.tiles_touched;
+        FDGS_STAGE(fdgs::launch_preprocess_fwd(pp, stream), "preprocess_fwd");
+        FDGS_STAGE(fdgs::launch_scan(geom.scan_temp, geom.scan_bytes, geom.tiles_touched, geom.point_offsets, P, stream),
+                   "scan");
+        // the one host synchronisation of the forward (reference: rasterizer_impl.cu:302)
+        FDGS_CUDA(cudaMemcpyAsync(&num_rendered, geom.point_offsets + (P - 1), sizeof(int), cudaMemcpyDeviceToHost, stream),
+                  "num_rendered copy");
+        FDGS_CUDA(cudaStreamSynchronize(stream), "num_rendered sync");
+    }
+    if (num_rendered < 0) return fail(FDGS_ERR_UNSUPPORTED, "more than 2^31 tile instances");
+    res->num_rendered = num_rendered;
+
+    const size_t bin_bytes = fdgs_binning_bytes(num_rendered, W, H);
+    char* bin_raw = binning_alloc(binning_ctx, bin_bytes);
+    if (!bin_raw) return fail(FDGS_ERR_ALLOC, "binning buffer allocation failed");
+    BinningState bin = BinningState::carve(align128(bin_raw), num_rendered);
+    res->binning_buffer = bin_raw;
+    res->binning_bytes = bin_bytes;
+
+    FDGS_CUDA(cudaMemsetAsync(img.ranges, 0, (size_t)grid_x * grid_y * sizeof(uint2), stream), "ranges memset");
+    if (num_rendered > 0) {
+        FDGS_STAGE(fdgs::launch_emit_keys(P, geom.means2D, geom.depths, geom.point_offsets, a->radii, grid_x, grid_y,
+                                          bin.keys_unsorted, bin.vals_unsorted, stream),
+                   "emit_keys");
+        int tile_bits = 0;
+        while ((1 << tile_bits) < grid_x * grid_y) ++tile_bits;
+        FDGS_STAGE(fdgs::launch_sort_pairs(bin.sort_temp, bin.sort_bytes, bin.keys_unsorted, bin.keys_sorted,
+                                           bin.vals_unsorted, bin.point_list, num_rendered, 32 + tile_bits, stream),
+                   "sort");
+        const float* colors = a->colors_precomp ? a->colors_precomp : geom.rgb;
+        FDGS_STAGE(fdgs::launch_pack_instances(num_rendered, bin.keys_sorted, bin.point_list, geom.means2D,
+                                               geom.conic_opacity, colors, geom.depths, a->flows_precomp, bin.recs,
+                                               img.ranges, stream),
+                   "pack_instances");
+    }
+    fdgs::BlendFwdParams bp;
+    bp.W = W; bp.H = H; bp.grid_x = grid_x; bp.grid_y = grid_y;
+    bp.ranges = img.ranges; bp.recs = bin.recs; bp.background = a->background;
+    bp.final_T = img.final_T; bp.n_contrib = img.n_contrib;
+    bp.out_color = a->out_color; bp.out_flow = a->out_flow; bp.out_depth = a->out_depth; bp.out_T = a->out_T;
+    (void)N;
+    FDGS_STAGE(fdgs::launch_blend_fwd(bp, stream), "blend_fwd");
+    return FDGS_OK;
+}
+
+int fdgs_backward(const fdgs_backward_args* a, void* stream_v) {
+    g_last_error.clear();
+    if (!a) return fail(FDGS_ERR_INVALID_ARG, "null argument");
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+    const bool debug = a->debug != 0;
+    const int P = a->P, W = a->width, H = a->height, R = a->R;
+    if (P <= 0) return FDGS_OK;
+    if (W <= 0 || H <= 0 || R < 0) return fail(FDGS_ERR_INVALID_ARG, "bad width / height / R");
+    if (!a->geom_buffer || !a->image_buffer || (R > 0 && !a->binning_buffer))
+        return fail(FDGS_ERR_INVALID_ARG, "scratch buffers of the forward pass required");
+    if (!a->dL_dpix || !a->dL_depths || !a->dL_masks || !a->dL_dpix_flow)
+        return fail(FDGS_ERR_INVALID_ARG, "pixel gradients required");
+    if (!a->dL_dmean2D || !a->dL_dconic || !a->dL_dopacity || !a->dL_dcolor || !a->dL_dflows || !a->dL_dmean3D ||
+        !a->dL_dcov3D || !a->dL_dts || !a->dL_dscale || !a->dL_dscale_t || !a->dL_drot || !a->dL_drot_r)
+        return fail(FDGS_ERR_INVALID_ARG, "gradient outputs required");
+    const int grid_x = (W + fdgs::TILE_X - 1) / fdgs::TILE_X, grid_y = (H + fdgs::TILE_Y - 1) / fdgs::TILE_Y;
+    GeomState geom = GeomState::carve(align128(const_cast<char*>(a->geom_buffer)), P);
+    ImageState img = ImageState::carve(align128(const_cast<char*>(a->image_buffer)), W, H);
+    BinningState bin = BinningState::carve(a->binning_buffer ? align128(const_cast<char*>(a->binning_buffer)) : nullptr, R);
+
+    if (R > 0) {
+        fdgs::BlendBwdParams bp;
+        bp.W = W; bp.H = H; bp.grid_x = grid_x; bp.grid_y = grid_y;
+        bp.ranges = img.ranges; bp.recs = bin.recs; bp.background = a->background;
+        bp.final_T = img.final_T; bp.n_contrib = img.n_contrib;
+        bp.dL_dpix = a->dL_dpix; bp.dL_depths = a->dL_depths; bp.dL_masks = a->dL_masks; bp.dL_dpix_flow = a->dL_dpix_flow;
+        bp.dL_dmean2D = a->dL_dmean2D; bp.dL_dconic = a->dL_dconic; bp.dL_dopacity = a->dL_dopacity;
+        bp.dL_dcolor = a->dL_dcolor; bp.dL_dflows = a->dL_dflows;
+        FDGS_STAGE(fdgs::launch_blend_bwd(bp, stream), "blend_bwd");
+    }
+    fdgs::PreprocessBwdParams pb;
+    memset(&pb, 0, sizeof(pb));
+    pb.P = P; pb.D = a->D; pb.D_t = a->D_t; pb.M = a->M;
+    pb.means3D = a->out_means3D; pb.radii = a->radii; pb.shs = a->shs; pb.ts = a->ts; pb.opacities = a->opacities;
+    pb.clamped = geom.clamped; pb.tiles_touched = geom.tiles_touched;
+    pb.scales = a->scales; pb.scales_t = a->scales_t; pb.rotations = a->rotations; pb.rotations_r = a->rotations_r;
+    pb.scale_modifier = a->scale_modifier;
+    pb.cov3D = a->cov3D_precomp ? a->cov3D_precomp : geom.cov3D;
+    pb.prefilter_var = a->prefilter_var; pb.viewmatrix = a->viewmatrix; pb.projmatrix = a->projmatrix;
+    pb.focal_y = H / (2.0f * a->tan_fovy);
+    pb.focal_x = W / (2.0f * a->tan_fovx);
+    pb.tan_fovx = a->tan_fovx; pb.tan_fovy = a->tan_fovy; pb.campos = a->campos;
+    pb.timestamp = a->timestamp; pb.time_duration = a->time_duration;
+    pb.rot_4d = a->rot_4d; pb.gaussian_dim = a->gaussian_dim; pb.force_sh_3d = a->force_sh_3d;
+    pb.has_scales = (a->scales != nullptr) ? 1 : 0;
+    sh_staging(a->shs, a->M, &pb.sh_bulk_ok, &pb.sh_row_stride_floats);
+    if (a->dL_dsh && (reinterpret_cast<uintptr_t>(a->dL_dsh) % 16) != 0) pb.sh_bulk_ok = 0;
+    pb.dL_dmean2D = a->dL_dmean2D; pb.dL_dconic = a->dL_dconic; pb.dL_dopacity = a->dL_dopacity; pb.dL_dcolor = a->dL_dcolor;
+    pb.dL_dmean3D = a->dL_dmean3D; pb.dL_dcov3D = a->dL_dcov3D; pb.dL_dsh = a->dL_dsh; pb.dL_dts = a->dL_dts;
+    pb.dL_dscale = a->dL_dscale; pb.dL_dscale_t = a->dL_dscale_t; pb.dL_drot = a->dL_drot; pb.dL_drot_r = a->dL_drot_r;
+    if (pb.has_scales && pb.rot_4d && (!a->rotations_r || !a->scales_t || !a->ts || !a->opacities))
+        return fail(FDGS_ERR_INVALID_ARG, "rot_4d backward needs rotations_r, scales_t, ts, opacities");
+    FDGS_STAGE(fdgs::launch_preprocess_bwd(pb, stream), "preprocess_bwd");
+    return FDGS_OK;
+}
+
+int fdgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float*, unsigned char* present,
+                      void* stream_v) {
+    g_last_error.clear();
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) return fail(FDGS_ERR_INVALID_ARG, "null argument");
+    FDGS_CUDA(fdgs::launch_mark_visible(P, means3D, viewmatrix, present, reinterpret_cast<cudaStream_t>(stream_v)),
+              "mark_visible");
+    return FDGS_OK;
+}
+
+int fdgs_debug_export_geom(const char* geom_buffer, int P, float* depths, float* means2D, float* conic_opacity,
+                           float* rgb, unsigned char* clamped, unsigned int* tiles_touched, void* stream_v) {
+    g_last_error.clear();
+    if (!geom_buffer || P <= 0) return fail(FDGS_ERR_INVALID_ARG, "null argument");
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+    GeomState g = GeomState::carve(align128(const_cast<char*>(geom_buffer)), P);
+    const size_t p = (size_t)P;
+    if (depths) FDGS_CUDA(cudaMemcpyAsync(depths, g.depths, p * 4, cudaMemcpyDeviceToDevice, stream), "export depths");
+    if (means2D) FDGS_CUDA(cudaMemcpyAsync(means2D, g.means2D, p * 8, cudaMemcpyDeviceToDevice, stream), "export means2D");
+    if (conic_opacity)
+        FDGS_CUDA(cudaMemcpyAsync(conic_opacity, g.conic_opacity, p * 16, cudaMemcpyDeviceToDevice, stream), "export conic");
+    if (rgb) FDGS_CUDA(cudaMemcpyAsync(rgb, g.rgb, p * 12, cudaMemcpyDeviceToDevice, stream), "export rgb");
+    if (clamped) FDGS_CUDA(cudaMemcpyAsync(clamped, g.clamped, p, cudaMemcpyDeviceToDevice, stream), "export clamped");
+    if (tiles_touched)
+        FDGS_CUDA(cudaMemcpyAsync(tiles_touched, g.tiles_touched, p * 4, cudaMemcpyDeviceToDevice, stream), "export tiles");
+    return FDGS_OK;
+}
+
+int fdgs_debug_export_binning(const char* binning_buffer, const char* image_buffer, int R, int W, int H,
+                              unsigned int* point_list, unsigned int* ranges, unsigned int* n_contrib, void* stream_v) {
+    g_last_error.clear();
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+    if (!image_buffer) return fail(FDGS_ERR_INVALID_ARG, "null argument");
+    ImageState img = ImageState::carve(align128(const_cast<char*>(image_buffer)), W, H);
+    const size_t tiles = (size_t)((W + fdgs::TILE_X - 1) / fdgs::TILE_X) * ((H + fdgs::TILE_Y - 1) / fdgs::TILE_Y);
+    if (point_list && R > 0) {
+        if (!binning_buffer) return fail(FDGS_ERR_INVALID_ARG, "null binning buffer");
+        BinningState b = BinningState::carve(align128(const_cast<char*>(binning_buffer)), R);
+        FDGS_CUDA(cudaMemcpyAsync(point_list, b.point_list, (size_t)R * 4, cudaMemcpyDeviceToDevice, stream),
+                  "export point_list");
+    }
+    if (ranges) FDGS_CUDA(cudaMemcpyAsync(ranges, img.ranges, tiles * 8, cudaMemcpyDeviceToDevice, stream), "export ranges");
+    if (n_contrib)
+        FDGS_CUDA(cudaMemcpyAsync(n_contrib, img.n_contrib, (size_t)W * H * 4, cudaMemcpyDeviceToDevice, stream),
+                  "export n_contrib");
+    return FDGS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,293 @@
+// fdgs_common.cuh -- shared device helpers of the B200-native 4D Gaussian rasterizer.
+//
+// Arithmetic contract.  "Tile assignment bit-exact" (BASELINE.json north_star) means the
+// per-Gaussian quantities that decide tiles, depth order and the blend thresholds must be
+// bit-identical to what the reference's kernels compute *as compiled by nvcc* (default
+// -fmad=true).  nvcc's mul+add -> fma contraction depends on use counts and inlining, so
+// this code does not rely on it: every operation on those paths is spelled with an explicit
+// round-to-nearest intrinsic (__fmul_rn / __fadd_rn / __fmaf_rn ... are never re-contracted),
+// in the association order read off the reference's PTX (tools/ptx2expr.py).  The CPU oracle
+// (oracle/fdgs_oracle.c) spells the same operations with fmaf()/plain ops under
+// -ffp-contract=off, so oracle and CUDA agree bit for bit except for MUFU.EX2.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fdgs {
+
+constexpr int TILE_X = 16;   // reference: config.h:16  BLOCK_X
+constexpr int TILE_Y = 16;   // reference: config.h:17  BLOCK_Y
+constexpr int TILE_PIX = TILE_X * TILE_Y;
+
+// ---- exact fp32 primitives -------------------------------------------------------------
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ float frcp(float a) { return __frcp_rn(a); }
+
+// a0*b0 + a1*b1 + a2*b2 as nvcc contracts a left-associated sum of single-use products:
+// the SECOND product stays a plain multiply, the first is fused onto it, the rest chain.
+__device__ __forceinline__ float dot3c(float a0, float b0, float a1, float b1, float a2, float b2) {
+    return ffma(a2, b2, ffma(a0, b0, fmul(a1, b1)));
+}
+__device__ __forceinline__ float dot4c(float a0, float b0, float a1, float b1, float a2, float b2,
+                                       float a3, float b3) {
+    return ffma(a3, b3, ffma(a2, b2, ffma(a0, b0, fmul(a1, b1))));
+}
+
+// reference: auxiliary.h:59-67 transformPoint4x3 / :69-78 transformPoint4x4, one row:
+// m[r]*x + m[4+r]*y + m[8+r]*z + m[12+r]  ->  m12 + fma(z, m8, fma(x, m0, y*m4))
+__device__ __forceinline__ float xform_row(float m0, float m4, float m8, float m12, float x, float y,
+                                           float z) {
+    return fadd(m12, ffma(z, m8, ffma(x, m0, fmul(y, m4))));
+}
+
+// Camera constants, loaded once per thread (broadcast through the constant/L1 path).
+struct Camera {
+    float view[16];
+    float proj[16];
+    float cam[3];
+};
+
+// ---- 4D covariance slice -----------------------------------------------------------------
+// reference: forward.cu:279-352 computeCov3D_conditional.  Produces the 10 distinct entries of
+// Sigma = (S R)^T (S R), R = M_r * M_l, in the reference's evaluation order.
+struct Sigma4 {
+    float s00, s01, s02, s03, s11, s12, s13, s22, s23, s33;
+    float M[4][4];   // M[c][r] = s_r * R[c][r]   (needed again by the backward)
+};
+
+template <bool WANT_R = false>
+__device__ __forceinline__ void build_M4(float sx, float sy, float sz, float st,  // already * mod
+                                         const float4 rot, const float4 rot_r, float M[4][4],
+                                         float (*Rout)[4] = nullptr) {
+    const float a = rot.x, b = rot.y, c = rot.z, d = rot.w;
+    const float p = rot_r.x, q = rot_r.y, r = rot_r.z, s = rot_r.w;
+    // glm column-major constructors, forward.cu:315-327
+    const float Ml[4][4] = {{a, b, -c, d}, {-b, a, d, c}, {c, -d, a, b}, {-d, -c, -b, a}};
+    const float Mr[4][4] = {{p, q, -r, -s}, {-q, p, s, -r}, {r, -s, p, -q}, {s, r, q, p}};
+    const float sc[4] = {sx, sy, sz, st};
+#pragma unroll
+    for (int col = 0; col < 4; ++col) {
+#pragma unroll
+        for (int row = 0; row < 4; ++row) {
+            // R = M_r * M_l (glm mat4*mat4, type_mat4x4.inl:630-648): plain products, left-assoc sum
+            float t = fmul(Mr[0][row], Ml[col][0]);
+            t = fadd(t, fmul(Mr[1][row], Ml[col][1]));
+            t = fadd(t, fmul(Mr[2][row], Ml[col][2]));
+            t = fadd(t, fmul(Mr[3][row], Ml[col][3]));
+            if (WANT_R) Rout[col][row] = t;
+            M[col][row] = fmul(sc[row], t);   // M = S * R, S diagonal
+        }
+    }
+}
+
+__device__ __forceinline__ float col_dot4(const float A[4], const float B[4]) {
+    // Sigma = transpose(M) * M: entry = sum_k A[k]*B[k], contracted as dot4c
+    return dot4c(A[0], B[0], A[1], B[1], A[2], B[2], A[3], B[3]);
+}
+
+__device__ __forceinline__ void sigma_from_M(Sigma4& S) {
+    S.s00 = col_dot4(S.M[0], S.M[0]);
+    S.s01 = col_dot4(S.M[1], S.M[0]);
+    S.s02 = col_dot4(S.M[2], S.M[0]);
+    S.s03 = col_dot4(S.M[3], S.M[0]);
+    S.s11 = col_dot4(S.M[1], S.M[1]);
+    S.s12 = col_dot4(S.M[2], S.M[1]);
+    S.s13 = col_dot4(S.M[3], S.M[1]);
+    S.s22 = col_dot4(S.M[2], S.M[2]);
+    S.s23 = col_dot4(S.M[3], S.M[2]);
+    S.s33 = col_dot4(S.M[3], S.M[3]);
+}
+
+// marginal_t = __expf(-0.5*dt*dt / cov_t')   reference: forward.cu:333 (double-promoted argument)
+__device__ __forceinline__ float marginal_from(float dt, float cov_t, float prefilter_var) {
+    const float den = (prefilter_var > 0.0f) ? fadd(prefilter_var, cov_t) : cov_t;
+    const double arg = ((double)dt * -0.5) * (double)dt / (double)den;
+    return __expf((float)arg);
+}
+
+// ---- 3D covariance -------------------------------------------------------------------------
+// reference: forward.cu:242-276 computeCov3D (quaternion NOT normalised, :251)
+__device__ __forceinline__ void build_M3(float sx, float sy, float sz, const float4 q, float M[3][3]) {
+    const float r = q.x, x = q.y, y = q.z, z = q.w;
+    const float yy = fmul(y, y), zz = fmul(z, z);
+    const float xy = fmul(x, y), rz = fmul(r, z), xz = fmul(x, z), ry = fmul(r, y);
+    const float yz = fmul(y, z), rx = fmul(r, x);
+    const float A = fadd(yy, zz);
+    const float B = ffma(x, x, zz);
+    const float C = ffma(x, x, yy);
+    float R[3][3];
+    float t;
+    R[0][0] = fsub(1.f, fadd(A, A));
+    t = fsub(xy, rz); R[0][1] = fadd(t, t);
+    t = fadd(xz, ry); R[0][2] = fadd(t, t);
+    t = fadd(xy, rz); R[1][0] = fadd(t, t);
+    R[1][1] = fsub(1.f, fadd(B, B));
+    t = fsub(yz, rx); R[1][2] = fadd(t, t);
+    t = fsub(xz, ry); R[2][0] = fadd(t, t);
+    t = fadd(yz, rx); R[2][1] = fadd(t, t);
+    R[2][2] = fsub(1.f, fadd(C, C));
+    const float sc[3] = {sx, sy, sz};
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr) M[c][rr] = fmul(sc[rr], R[c][rr]);
+}
+
+__device__ __forceinline__ void cov3_from_M3(const float M[3][3], float cov[6]) {
+    cov[0] = dot3c(M[0][0], M[0][0], M[0][1], M[0][1], M[0][2], M[0][2]);
+    cov[1] = dot3c(M[1][0], M[0][0], M[1][1], M[0][1], M[1][2], M[0][2]);
+    cov[2] = dot3c(M[2][0], M[0][0], M[2][1], M[0][1], M[2][2], M[0][2]);
+    cov[3] = dot3c(M[1][0], M[1][0], M[1][1], M[1][1], M[1][2], M[1][2]);
+    cov[4] = dot3c(M[2][0], M[1][0], M[2][1], M[1][1], M[2][2], M[1][2]);
+    cov[5] = dot3c(M[2][0], M[2][0], M[2][1], M[2][1], M[2][2], M[2][2]);
+}
+
+// ---- EWA projection ------------------------------------------------------------------------
+// reference: forward.cu:198-237 computeCov2D (forward) and backward.cu:507-537 (recompute).
+// T = W * J (only the two non-zero columns), then cov = T^T Vrk^T T.
+struct Proj2D {
+    float T00, T01, T02, T10, T11, T12;   // T[c][r]
+    float tx, ty, tz;                     // clamped view-space mean
+    float txtz, tytz;
+};
+
+__device__ __forceinline__ void build_T(const float* __restrict__ view, float mx, float my, float mz,
+                                        float focal_x, float focal_y, float tan_fovx, float tan_fovy,
+                                        Proj2D& P) {
+    const float tx0 = xform_row(view[0], view[4], view[8], view[12], mx, my, mz);
+    const float ty0 = xform_row(view[1], view[5], view[9], view[13], mx, my, mz);
+    const float tz = xform_row(view[2], view[6], view[10], view[14], mx, my, mz);
+    const float limx = fmul(1.3f, tan_fovx);
+    const float limy = fmul(1.3f, tan_fovy);
+    P.txtz = fdiv(tx0, tz);
+    P.tytz = fdiv(ty0, tz);
+    // min(limx, max(-limx, txtz)) * t.z   (forward.cu:210-211)
+    P.tx = fmul(fminf(limx, fmaxf(-limx, P.txtz)), tz);
+    P.ty = fmul(fminf(limy, fmaxf(-limy, P.tytz)), tz);
+    P.tz = tz;
+    const float tz2 = fmul(tz, tz);
+    const float j00 = fdiv(focal_x, tz);
+    const float j11 = fdiv(focal_y, tz);
+    const float j02 = fdiv(fmul(focal_x, -P.tx), tz2);   // -(focal_x * t.x) / (t.z * t.z)
+    const float j12 = fdiv(fmul(focal_y, -P.ty), tz2);
+    P.T00 = ffma(view[2], j02, fmul(view[0], j00));
+    P.T01 = ffma(view[6], j02, fmul(view[4], j00));
+    P.T02 = ffma(j02, view[10], fmul(view[8], j00));
+    P.T10 = ffma(view[2], j12, fmul(j11, view[1]));
+    P.T11 = ffma(view[6], j12, fmul(j11, view[5]));
+    P.T12 = ffma(j12, view[10], fmul(j11, view[9]));
+}
+
+// cov2D (before the +0.3 low-pass): a = cov[0][0], b = cov[0][1], c = cov[1][1]
+__device__ __forceinline__ void cov2d_from_T(const Proj2D& P, const float c3[6], float& a, float& b,
+                                             float& c) {
+    const float X00 = dot3c(P.T00, c3[0], P.T01, c3[1], P.T02, c3[2]);
+    const float X01 = dot3c(P.T10, c3[0], P.T11, c3[1], P.T12, c3[2]);
+    const float X10 = dot3c(P.T00, c3[1], P.T01, c3[3], P.T02, c3[4]);
+    const float X11 = dot3c(P.T10, c3[1], P.T11, c3[3], P.T12, c3[4]);
+    const float X20 = dot3c(P.T00, c3[2], P.T01, c3[4], P.T02, c3[5]);
+    const float X21 = dot3c(P.T10, c3[2], P.T11, c3[4], P.T12, c3[5]);
+    a = dot3c(P.T00, X00, P.T01, X10, P.T02, X20);
+    b = dot3c(P.T00, X01, P.T01, X11, P.T02, X21);
+    c = dot3c(P.T10, X01, P.T11, X11, P.T12, X21);
+}
+
+// reference: auxiliary.h:42-45 ndc2Pix -- evaluated in double, contracted to a double fma
+__device__ __forceinline__ float ndc2pix(float v, int S) {
+    return (float)(__fma_rn((double)v + 1.0, (double)S, -1.0) * 0.5);
+}
+
+// reference: auxiliary.h:47-57 getRect (max_radius is an int there)
+__device__ __forceinline__ void get_rect(float px, float py, int radius, int gx, int gy, int& x0, int& y0,
+                                         int& x1, int& y1) {
+    const float r = (float)radius;
+    x0 = min(gx, max(0, (int)fmul(fsub(px, r), 0.0625f)));
+    y0 = min(gy, max(0, (int)fmul(fsub(py, r), 0.0625f)));
+    x1 = min(gx, max(0, (int)fmul(fadd(fadd(fadd(px, r), 16.0f), -1.0f), 0.0625f)));
+    y1 = min(gy, max(0, (int)fmul(fadd(fadd(fadd(py, r), 16.0f), -1.0f), 0.0625f)));
+}
+
+// SH constants, reference: auxiliary.h:23-40
+__device__ constexpr float kSH_C0 = 0.28209479177387814f;
+__device__ constexpr float kSH_C1 = 0.4886025119029199f;
+__device__ constexpr float kSH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                        -1.0925484305920792f, 0.5462742152960396f};
+__device__ constexpr float kSH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                        0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                                        -0.5900435899266435f};
+#define FDGS_MY_PI 3.14159265   /* double literal, reference: auxiliary.h:20 */
+
+// ---- per-instance record consumed by the blend kernels -------------------------------------
+// One 64-byte record per (tile, Gaussian) instance, stored in tile-sorted order, so that a
+// tile's work list is one contiguous byte range that cp.async.bulk can stream into shared
+// memory.  Four float4 "planes":
+//   q0 = { x, y, pmin, gaussian_id (bits) }   pixel-space mean; pmin = log(1/(255*opacity)) - slack
+//   q1 = { A, B, C, opacity }                 conic (reference conic_opacity)
+//   q2 = { r, g, b, depth }
+//   q3 = { flow_x, flow_y, ex, ey }           ex/ey = half-extents of the alpha >= 1/255 box
+struct __align__(16) InstRec {
+    float4 q0, q1, q2, q3;
+};
+static_assert(sizeof(InstRec) == 64, "InstRec must be 64 bytes");
+
+// ---- mbarrier / bulk-copy (TMA 1-D) PTX wrappers ----------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// global -> shared bulk copy (SASS: UBLKCP), completion signalled on `bar` (complete_tx::bytes).
+// dst, src and bytes must be multiples of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+// shared -> global bulk copy (bulk async-group completion)
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// make generic-proxy smem writes visible to the async proxy before a bulk store reads them
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+}  // namespace fdgs

@@ -1,0 +1,389 @@
+// preprocess_fwd.cu -- per-Gaussian forward preprocessing (one thread per Gaussian).
+//
+// Replaces the reference's preprocessCUDA<3> (forward.cu:355-496) together with its helpers
+// computeCov3D_conditional (:279-352), computeCov3D (:242-276), computeCov2D (:198-237),
+// computeColorFromSH (:20-71) / computeColorFromSH_4D (:73-195), in_frustum
+// (auxiliary.h:140-163), ndc2Pix (:42-45) and getRect (:47-57).
+//
+// B200 design:
+//   * geometry inputs (68 B/Gaussian) are read with coalesced 32/128-bit loads;
+//   * the 12*M-byte SH row of every *visible* Gaussian is streamed global->shared with one
+//     cp.async.bulk (TMA 1-D, SASS UBLKCP) per row, all rows of a block completing on one
+//     mbarrier; rows sit at a padded 16-byte-aligned stride so that the per-thread LDS.128
+//     reads are bank-conflict free; no register staging, no 12-byte strided LDG;
+//   * out_means3D is written for every Gaussian here (the reference clones means3D first,
+//     rasterize_points.cu:85, and overwrites the time-visible rows).
+// All arithmetic that feeds radii / tiles / depth / conic / rgb follows the reference bit for
+// bit (see fdgs_common.cuh).
+#include "fdgs_internal.h"
+
+namespace fdgs {
+
+namespace {
+
+constexpr int PRE_THREADS = 128;
+
+struct ShBasis {
+    float l[16];   // l0m0, l1m1, l1m0, l1p1, l2m2 .. l3p3
+};
+
+// reference: forward.cu:79-131 (4D variant; the double-promoted l2m0 and integer literals)
+__device__ __forceinline__ void sh_basis_4d(float x, float y, float z, int deg, ShBasis& B) {
+    B.l[0] = kSH_C0;
+    if (deg > 0) {
+        B.l[1] = fmul(y, -kSH_C1);
+        B.l[2] = fmul(z, kSH_C1);
+        B.l[3] = fmul(x, -kSH_C1);
+        if (deg > 1) {
+            const float xx = fmul(x, x), yy = fmul(y, y), zz = fmul(z, z);
+            const float xy = fmul(x, y), yz = fmul(y, z), xz = fmul(x, z);
+            B.l[4] = fmul(xy, kSH_C2[0]);
+            B.l[5] = fmul(yz, kSH_C2[1]);
+            // SH_C2[2] * (2.0 * zz - xx - yy): double (forward.cu:112)
+            B.l[6] = (float)(((((double)zz + (double)zz) - (double)xx) - (double)yy) * (double)kSH_C2[2]);
+            B.l[7] = fmul(xz, kSH_C2[3]);
+            B.l[8] = fmul(fsub(xx, yy), kSH_C2[4]);
+            if (deg > 2) {
+                B.l[9] = fmul(fmul(y, kSH_C3[0]), fsub(fmul(xx, 3.f), yy));
+                B.l[10] = fmul(z, fmul(xy, kSH_C3[1]));
+                B.l[11] = fmul(fmul(y, kSH_C3[2]), fsub(fsub(fmul(zz, 4.f), xx), yy));
+                B.l[12] = fmul(fmul(z, kSH_C3[3]), fsub(fsub(fadd(zz, zz), fmul(xx, 3.f)), fmul(yy, 3.f)));
+                B.l[13] = fmul(fmul(x, kSH_C3[4]), fsub(fsub(fmul(zz, 4.f), xx), yy));
+                B.l[14] = fmul(fmul(z, kSH_C3[5]), fsub(xx, yy));
+                B.l[15] = fmul(fmul(x, kSH_C3[6]), fsub(xx, fmul(yy, 3.f)));
+            }
+        }
+    }
+}
+
+// Row access: v[3*i + ch] = coefficient (16*blk + i), channel ch.
+struct RowSmem {
+    const float4* q;   // padded shared-memory row, 16-byte aligned
+    __device__ __forceinline__ void load_block(int blk, int /*M*/, float v[48]) const {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            const float4 t = q[blk * 12 + i];
+            v[4 * i + 0] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        }
+    }
+};
+struct RowGmem {
+    const float* p;   // global row (any alignment, any M)
+    __device__ __forceinline__ void load_block(int blk, int M, float v[48]) const {
+#pragma unroll
+        for (int i = 0; i < 48; ++i) {
+            const int k = blk * 48 + i;
+            v[i] = (k < 3 * M) ? __ldg(p + k) : 0.f;
+        }
+    }
+};
+
+// reference: forward.cu:73-195 computeColorFromSH_4D.  Returns result BEFORE the +0.5/clamp.
+template <class Row>
+__device__ __forceinline__ void sh_color_4d(const Row& row, int M, int deg, int deg_t, float x, float y, float z,
+                                            float dir_t, float time_duration, float rgb[3]) {
+    ShBasis B;
+    sh_basis_4d(x, y, z, deg, B);
+    float v[48];
+    row.load_block(0, M, v);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float r = fmul(v[ch], kSH_C0);
+        if (deg > 0) {
+            r = fadd(r, ffma(B.l[3], v[9 + ch], ffma(B.l[1], v[3 + ch], fmul(B.l[2], v[6 + ch]))));
+            if (deg > 1) {
+                float b = ffma(B.l[4], v[12 + ch], fmul(B.l[5], v[15 + ch]));
+                b = ffma(v[18 + ch], B.l[6], b);
+                b = ffma(B.l[8], v[24 + ch], ffma(B.l[7], v[21 + ch], b));
+                r = fadd(r, b);
+                if (deg > 2) {
+                    float c = ffma(B.l[11], v[33 + ch], ffma(B.l[9], v[27 + ch], fmul(B.l[10], v[30 + ch])));
+                    c = ffma(B.l[13], v[39 + ch], ffma(B.l[12], v[36 + ch], c));
+                    c = ffma(B.l[15], v[45 + ch], ffma(B.l[14], v[42 + ch], c));
+                    r = fadd(r, c);
+                }
+            }
+        }
+        rgb[ch] = r;
+    }
+    // temporal Fourier terms only exist under deg > 2 (forward.cu:142 nested in :123)
+    if (deg > 2 && deg_t > 0) {
+        const double ang = ((double)dir_t * (2 * FDGS_MY_PI)) / (double)time_duration;
+        const float t1 = (float)cos(ang);
+        row.load_block(1, M, v);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            float s = ffma(v[ch], B.l[0], fmul(B.l[1], v[3 + ch]));
+#pragma unroll
+            for (int k = 2; k < 16; ++k) s = ffma(B.l[k], v[3 * k + ch], s);
+            rgb[ch] = ffma(s, t1, rgb[ch]);
+        }
+        if (deg_t > 1) {
+            const double ang2 = (((double)dir_t * (2 * FDGS_MY_PI)) * 2.0) / (double)time_duration;
+            const float t2 = (float)cos(ang2);
+            row.load_block(2, M, v);
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                float s = ffma(v[ch], B.l[0], fmul(B.l[1], v[3 + ch]));
+#pragma unroll
+                for (int k = 2; k < 16; ++k) s = ffma(B.l[k], v[3 * k + ch], s);
+                rgb[ch] = ffma(s, t2, rgb[ch]);
+            }
+        }
+    }
+}
+
+// reference: forward.cu:20-71 computeColorFromSH (3D).  Returns result BEFORE the +0.5/clamp.
+template <class Row>
+__device__ __forceinline__ void sh_color_3d(const Row& row, int M, int deg, float x, float y, float z,
+                                            float rgb[3]) {
+    float v[48];
+    row.load_block(0, M, v);
+    const float xx = fmul(x, x), yy = fmul(y, y), zz = fmul(z, z);
+    const float xy = fmul(x, y), yz = fmul(y, z), xz = fmul(x, z);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float r = fmul(v[ch], kSH_C0);
+        if (deg > 0) {
+            // result - C1*y*sh1 + C1*z*sh2 - C1*x*sh3
+            r = fsub(r, fmul(fmul(y, kSH_C1), v[3 + ch]));
+            r = ffma(fmul(z, kSH_C1), v[6 + ch], r);
+            r = fsub(r, fmul(fmul(x, kSH_C1), v[9 + ch]));
+            if (deg > 1) {
+                r = ffma(fmul(xy, kSH_C2[0]), v[12 + ch], r);
+                r = ffma(fmul(yz, kSH_C2[1]), v[15 + ch], r);
+                r = ffma(fmul(fsub(fsub(fadd(zz, zz), xx), yy), kSH_C2[2]), v[18 + ch], r);
+                r = ffma(fmul(xz, kSH_C2[3]), v[21 + ch], r);
+                r = ffma(fmul(fsub(xx, yy), kSH_C2[4]), v[24 + ch], r);
+                if (deg > 2) {
+                    r = ffma(fmul(fmul(y, kSH_C3[0]), fsub(fmul(xx, 3.f), yy)), v[27 + ch], r);
+                    r = ffma(fmul(z, fmul(xy, kSH_C3[1])), v[30 + ch], r);
+                    r = ffma(fmul(fmul(y, kSH_C3[2]), fsub(fsub(fmul(zz, 4.f), xx), yy)), v[33 + ch], r);
+                    r = ffma(fmul(fmul(z, kSH_C3[3]), fsub(fsub(fadd(zz, zz), fmul(xx, 3.f)), fmul(yy, 3.f))),
+                             v[36 + ch], r);
+                    r = ffma(fmul(fmul(x, kSH_C3[4]), fsub(fsub(fmul(zz, 4.f), xx), yy)), v[39 + ch], r);
+                    r = ffma(fmul(fmul(z, kSH_C3[5]), fsub(xx, yy)), v[42 + ch], r);
+                    r = ffma(fmul(fmul(x, kSH_C3[6]), fsub(xx, fmul(yy, 3.f))), v[45 + ch], r);
+                }
+            }
+        }
+        rgb[ch] = r;
+    }
+}
+
+template <bool BULK>
+__global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreprocessFwdParams a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+
+    const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
+    const bool in_range = idx < a.P;
+    if (BULK) {
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+    }
+
+    bool visible = false;
+    float depth = 0.f, px = 0.f, py = 0.f, opacity = 0.f;
+    float conx = 0.f, cony = 0.f, conz = 0.f;
+    int radius = 0;
+    uint32_t tiles = 0;
+    float mx = 0.f, my = 0.f, mz = 0.f;   // (shifted) mean
+    float ox = 0.f, oy = 0.f, oz = 0.f;   // original mean (SH view direction, quirk: forward.cu:480,482)
+
+    if (in_range) {
+        ox = mx = a.means3D[3 * idx + 0];
+        oy = my = a.means3D[3 * idx + 1];
+        oz = mz = a.means3D[3 * idx + 2];
+        opacity = a.opacities[idx];
+        bool alive = true;
+        float c3[6];
+        if (a.cov3D_precomp != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) c3[i] = a.cov3D_precomp[6 * idx + i];
+        } else if (a.rot_4d) {
+            // forward.cu:279-352
+            const float dt = fsub(a.timestamp, a.ts[idx]);
+            const float4 rot = reinterpret_cast<const float4*>(a.rotations)[idx];
+            const float4 rotr = reinterpret_cast<const float4*>(a.rotations_r)[idx];
+            Sigma4 S;
+            build_M4(fmul(a.scale_modifier, a.scales[3 * idx + 0]), fmul(a.scale_modifier, a.scales[3 * idx + 1]),
+                     fmul(a.scale_modifier, a.scales[3 * idx + 2]), fmul(a.scale_modifier, a.scales_t[idx]), rot,
+                     rotr, S.M);
+            sigma_from_M(S);
+            const float cov_t = S.s33;
+            const float marginal = marginal_from(dt, cov_t, a.prefilter_var);
+            if (!((double)marginal > 0.05)) {
+                alive = false;
+            } else {
+                opacity = fmul(opacity, marginal);
+                c3[0] = fsub(S.s00, fdiv(fmul(S.s03, S.s03), cov_t));
+                c3[1] = fsub(S.s01, fdiv(fmul(S.s13, S.s03), cov_t));
+                c3[2] = fsub(S.s02, fdiv(fmul(S.s23, S.s03), cov_t));
+                c3[3] = fsub(S.s11, fdiv(fmul(S.s13, S.s13), cov_t));
+                c3[4] = fsub(S.s12, fdiv(fmul(S.s23, S.s13), cov_t));
+                c3[5] = fsub(S.s22, fdiv(fmul(S.s23, S.s23), cov_t));
+                mx = ffma(dt, fdiv(S.s03, cov_t), mx);
+                my = ffma(dt, fdiv(S.s13, cov_t), my);
+                mz = ffma(dt, fdiv(S.s23, cov_t), mz);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) a.cov3D[6 * idx + i] = c3[i];
+            }
+        } else {
+            // forward.cu:242-276 and :431-437
+            float M3[3][3];
+            build_M3(fmul(a.scale_modifier, a.scales[3 * idx + 0]), fmul(a.scale_modifier, a.scales[3 * idx + 1]),
+                     fmul(a.scale_modifier, a.scales[3 * idx + 2]), reinterpret_cast<const float4*>(a.rotations)[idx],
+                     M3);
+            cov3_from_M3(M3, c3);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) a.cov3D[6 * idx + i] = c3[i];
+            if (a.gaussian_dim == 4) {
+                const float dt = fsub(a.ts[idx], a.timestamp);
+                const float sigma = fmul(a.scale_modifier, a.scales_t[idx]);
+                const float marginal = marginal_from(dt, sigma, a.prefilter_var);
+                if ((double)marginal <= 0.05) alive = false;
+                else opacity = fmul(opacity, marginal);
+            }
+        }
+        // out_means3D: every row (shifted where the time slice applied)
+        a.out_means3D[3 * idx + 0] = mx;
+        a.out_means3D[3 * idx + 1] = my;
+        a.out_means3D[3 * idx + 2] = mz;
+
+        if (alive) {
+            const float* V = a.viewmatrix;
+            const float* Pm = a.projmatrix;
+            // in_frustum: auxiliary.h:140-163 (only the view-z test is live)
+            const float vz = xform_row(V[2], V[6], V[10], V[14], mx, my, mz);
+            if (vz <= 0.2f) {
+                alive = false;
+                if (a.prefiltered) {
+                    printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+                    __trap();
+                }
+            } else {
+                depth = vz;
+                const float hx = xform_row(Pm[0], Pm[4], Pm[8], Pm[12], mx, my, mz);
+                const float hy = xform_row(Pm[1], Pm[5], Pm[9], Pm[13], mx, my, mz);
+                const float hw = xform_row(Pm[3], Pm[7], Pm[11], Pm[15], mx, my, mz);
+                const float p_w = frcp(fadd(hw, 0.0000001f));
+                const float projx = fmul(hx, p_w), projy = fmul(hy, p_w);
+
+                Proj2D Pj;
+                build_T(V, mx, my, mz, a.focal_x, a.focal_y, a.tan_fovx, a.tan_fovy, Pj);
+                float ca, cb, cc;
+                cov2d_from_T(Pj, c3, ca, cb, cc);
+                ca = fadd(ca, 0.3f);
+                cc = fadd(cc, 0.3f);
+                const float bb = fmul(cb, cb);
+                const float det = fsub(fmul(ca, cc), bb);
+                if (det == 0.0f) {
+                    alive = false;
+                } else {
+                    const float det_inv = frcp(det);
+                    conx = fmul(cc, det_inv);
+                    cony = fmul(det_inv, -cb);
+                    conz = fmul(ca, det_inv);
+                    const float mid = fmul(fadd(ca, cc), 0.5f);
+                    const float sq = fsqrt(fmaxf(fsub(fmul(mid, mid), det), 0.1f));
+                    const float lam = fmaxf(fadd(mid, sq), fsub(mid, sq));
+                    const float my_radius = ceilf(fmul(fsqrt(lam), 3.f));
+                    px = ndc2pix(projx, a.W);
+                    py = ndc2pix(projy, a.H);
+                    radius = (int)my_radius;
+                    int x0, y0, x1, y1;
+                    get_rect(px, py, radius, a.grid_x, a.grid_y, x0, y0, x1, y1);
+                    tiles = (uint32_t)((x1 - x0) * (y1 - y0));
+                    if (tiles == 0 || radius < 1) alive = false;
+                }
+            }
+        }
+        visible = alive;
+    }
+
+    // ---- colour ------------------------------------------------------------------------------
+    const bool need_sh = (a.colors_precomp == nullptr);
+    float rgb[3] = {0.f, 0.f, 0.f};
+    uint8_t clamp_bits = 0;
+    if (need_sh) {
+        const int row_floats = 3 * a.M;
+        if (BULK) {
+            const int nvis = __syncthreads_count(visible);
+            float* rows = reinterpret_cast<float*>(smem_raw);
+            const int stride = a.sh_row_stride_floats;   // padded, multiple of 4
+            if (threadIdx.x == 0 && nvis > 0) mbar_expect_tx(&bar, (uint32_t)nvis * (uint32_t)row_floats * 4u);
+            if (visible)
+                bulk_g2s(rows + (size_t)threadIdx.x * stride, a.shs + (size_t)idx * row_floats,
+                         (uint32_t)row_floats * 4u, &bar);
+            if (visible) mbar_wait(&bar, 0);
+        }
+        if (visible) {
+            const float dx = fsub(ox, a.cam_pos[0]), dy = fsub(oy, a.cam_pos[1]), dz = fsub(oz, a.cam_pos[2]);
+            const float len = fsqrt(ffma(dz, dz, ffma(dx, dx, fmul(dy, dy))));
+            const float x = fdiv(dx, len), y = fdiv(dy, len), z = fdiv(dz, len);
+            const bool sh3d = (a.gaussian_dim == 3) || a.force_sh_3d;
+            if (BULK) {
+                RowSmem row{reinterpret_cast<const float4*>(reinterpret_cast<float*>(smem_raw) +
+                                                            (size_t)threadIdx.x * a.sh_row_stride_floats)};
+                if (sh3d) sh_color_3d(row, a.M, a.D, x, y, z, rgb);
+                else sh_color_4d(row, a.M, a.D, a.D_t, x, y, z, fsub(a.ts[idx], a.timestamp), a.time_duration, rgb);
+            } else {
+                RowGmem row{a.shs + (size_t)idx * row_floats};
+                if (sh3d) sh_color_3d(row, a.M, a.D, x, y, z, rgb);
+                else sh_color_4d(row, a.M, a.D, a.D_t, x, y, z, fsub(a.ts[idx], a.timestamp), a.time_duration, rgb);
+            }
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const float r = fadd(rgb[ch], 0.5f);
+                if (r < 0.f) { clamp_bits |= (1u << ch); rgb[ch] = 0.f; }
+                else rgb[ch] = r;
+            }
+        }
+    } else if (visible) {
+        rgb[0] = a.colors_precomp[3 * idx + 0];
+        rgb[1] = a.colors_precomp[3 * idx + 1];
+        rgb[2] = a.colors_precomp[3 * idx + 2];
+    }
+
+    if (in_range) {
+        a.radii[idx] = visible ? radius : 0;
+        a.tiles_touched[idx] = visible ? tiles : 0u;
+        if (visible) {
+            a.depths[idx] = depth;
+            reinterpret_cast<float2*>(a.means2D)[idx] = make_float2(px, py);
+            reinterpret_cast<float4*>(a.conic_opacity)[idx] = make_float4(conx, cony, conz, opacity);
+            a.rgb[3 * idx + 0] = rgb[0];
+            a.rgb[3 * idx + 1] = rgb[1];
+            a.rgb[3 * idx + 2] = rgb[2];
+            a.clamped[idx] = clamp_bits;
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_preprocess_fwd(const PreprocessFwdParams& p, cudaStream_t stream) {
+    if (p.P <= 0) return cudaSuccess;
+    const int blocks = (p.P + PRE_THREADS - 1) / PRE_THREADS;
+    const bool bulk = p.sh_bulk_ok && p.colors_precomp == nullptr;
+    if (bulk) {
+        const size_t smem = (size_t)PRE_THREADS * p.sh_row_stride_floats * sizeof(float);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(preprocess_fwd_kernel<true>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return e;
+            attr_set = true;
+        }
+        preprocess_fwd_kernel<true><<<blocks, PRE_THREADS, smem, stream>>>(p);
+    } else {
+        preprocess_fwd_kernel<false><<<blocks, PRE_THREADS, 0, stream>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace fdgs

@@ -1,0 +1,260 @@
+// torch_ext.cpp -- thin PyTorch shim over the fdgs C-ABI (include/fdgs.h).
+//
+// Exposes the same three functions, with the same positional arguments and return tuples, as
+// the reference's extension module (reference: diff-gaussian-rasterization/ext.cpp:15-19,
+// rasterize_points.h:18-93, rasterize_points.cu:36-291), so that the reference's own
+// gaussian_renderer/diff_gaussian_rasterization.py could be pointed at this module unchanged:
+//
+//   rasterize_gaussians(30 args)          -> (num_rendered, color, flow, depth, T, radii,
+//                                             geomBuffer, binningBuffer, imgBuffer, covs3D_com, out_means3D)
+//   rasterize_gaussians_backward(37 args) -> 12 gradient tensors
+//   mark_visible(means3D, viewmatrix, projmatrix) -> bool[P]
+//
+// PyTorch is plumbing only: it owns the memory (tensors, the three growable byte buffers handed
+// to the library through the allocation callback) and supplies the current CUDA stream.  No
+// arithmetic happens here.  Differences from the reference shim, all performance-motivated and
+// invisible to callers: outputs are torch::empty (the kernels write every element; the
+// reference zero-fills 7 image planes in forward and 716 B/Gaussian in backward), out_means3D is
+// written by the preprocess kernel instead of cloned, covs3D_com is an owning view into
+// geomBuffer instead of a dangling from_blob alias (reference: rasterize_points.cu:147), and
+// launches go to the current stream instead of the legacy default stream.
+#include <torch/extension.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+#include <tuple>
+#include "../../include/fdgs.h"
+
+namespace {
+
+char* resize_cb(void* ctx, size_t bytes) {
+    auto* t = reinterpret_cast<torch::Tensor*>(ctx);
+    t->resize_({(long long)bytes});
+    return reinterpret_cast<char*>(t->data_ptr());
+}
+
+const float* fptr(const torch::Tensor& t) {
+    // empty tensor == "not provided" (reference: diff_gaussian_rasterization.py:282-300)
+    if (!t.defined() || t.numel() == 0) return nullptr;
+    TORCH_CHECK(t.is_cuda(), "fdgs: expected a CUDA tensor");
+    TORCH_CHECK(t.scalar_type() == torch::kFloat32, "fdgs: expected a float32 tensor");
+    return t.data_ptr<float>();
+}
+
+torch::Tensor contig(const torch::Tensor& t) { return (t.defined() && t.numel() > 0) ? t.contiguous() : t; }
+
+void check(int rc, const char* where) {
+    if (rc != FDGS_OK) throw std::runtime_error(std::string("fdgs ") + where + " failed: " + fdgs_last_error());
+}
+
+}  // namespace
+
+std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
+           torch::Tensor, torch::Tensor, torch::Tensor>
+RasterizeGaussiansCUDA(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& colors,
+                       const torch::Tensor& flows, const torch::Tensor& opacity, const torch::Tensor& ts,
+                       const torch::Tensor& scales, const torch::Tensor& scales_t, const torch::Tensor& rotations,
+                       const torch::Tensor& rotations_r, const float scale_modifier, const torch::Tensor& cov3D_precomp,
+                       const float prefilter_var, const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix,
+                       const float tan_fovx, const float tan_fovy, const int image_height, const int image_width,
+                       const torch::Tensor& sh, const int degree, const int degree_t, const torch::Tensor& campos,
+                       const float timestamp, const float time_duration, const bool rot_4d, const int gaussian_dim,
+                       const bool force_sh_3d, const bool prefiltered, const bool debug) {
+    if (means3D.ndimension() != 2 || means3D.size(1) != 3) {
+        AT_ERROR("means3D must have dimensions (num_points, 3)");   // reference: rasterize_points.cu:69-71
+    }
+    TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor");
+    const c10::cuda::CUDAGuard guard(means3D.device());
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream().stream();
+
+    const int P = means3D.size(0);
+    const int H = image_height, W = image_width;
+    auto fopts = means3D.options().dtype(torch::kFloat32);
+    auto iopts = means3D.options().dtype(torch::kInt32);
+    auto bopts = means3D.options().dtype(torch::kByte);
+
+    torch::Tensor out_color = torch::empty({3, H, W}, fopts);
+    torch::Tensor out_flow = torch::empty({2, H, W}, fopts);
+    torch::Tensor out_depth = torch::empty({1, H, W}, fopts);
+    torch::Tensor out_T = torch::empty({1, H, W}, fopts);
+    torch::Tensor radii = torch::empty({P}, iopts);
+    torch::Tensor out_means3D = torch::empty({P, 3}, fopts);
+    torch::Tensor geomBuffer = torch::empty({0}, bopts);
+    torch::Tensor binningBuffer = torch::empty({0}, bopts);
+    torch::Tensor imgBuffer = torch::empty({0}, bopts);
+
+    // keep contiguous copies alive for the duration of the call
+    const auto bg_c = contig(background), means_c = contig(means3D), col_c = contig(colors), flow_c = contig(flows),
+               op_c = contig(opacity), ts_c = contig(ts), sc_c = contig(scales), sct_c = contig(scales_t),
+               rot_c = contig(rotations), rotr_c = contig(rotations_r), cov_c = contig(cov3D_precomp),
+               view_c = contig(viewmatrix), proj_c = contig(projmatrix), sh_c = contig(sh), cam_c = contig(campos);
+
+    fdgs_forward_args a;
+    memset(&a, 0, sizeof(a));
+    a.P = P; a.D = degree; a.D_t = degree_t;
+    a.M = (sh.defined() && sh.numel() != 0) ? (int)sh.size(1) : 0;
+    a.background = fptr(bg_c); a.width = W; a.height = H;
+    a.means3D = fptr(means_c); a.shs = fptr(sh_c); a.colors_precomp = fptr(col_c); a.flows_precomp = fptr(flow_c);
+    a.opacities = fptr(op_c); a.ts = fptr(ts_c); a.scales = fptr(sc_c); a.scales_t = fptr(sct_c);
+    a.scale_modifier = scale_modifier; a.rotations = fptr(rot_c); a.rotations_r = fptr(rotr_c);
+    a.cov3D_precomp = fptr(cov_c); a.prefilter_var = prefilter_var;
+    a.viewmatrix = fptr(view_c); a.projmatrix = fptr(proj_c); a.cam_pos = fptr(cam_c);
+    a.timestamp = timestamp; a.time_duration = time_duration; a.rot_4d = rot_4d; a.gaussian_dim = gaussian_dim;
+    a.force_sh_3d = force_sh_3d; a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy; a.prefiltered = prefiltered;
+    a.debug = debug;
+    a.out_means3D = out_means3D.data_ptr<float>(); a.out_color = out_color.data_ptr<float>();
+    a.out_flow = out_flow.data_ptr<float>(); a.out_depth = out_depth.data_ptr<float>();
+    a.out_T = out_T.data_ptr<float>(); a.radii = radii.data_ptr<int>();
+
+    fdgs_forward_result r;
+    check(fdgs_forward(&a, resize_cb, &geomBuffer, resize_cb, &binningBuffer, resize_cb, &imgBuffer, (void*)stream, &r),
+          "forward");
+
+    torch::Tensor covs3D_com;
+    if (P > 0) {
+        const int64_t off = reinterpret_cast<const char*>(r.cov3D) - reinterpret_cast<const char*>(geomBuffer.data_ptr());
+        covs3D_com = geomBuffer.narrow(0, off, (int64_t)P * 24).view(torch::kFloat32).view({P, 6});
+    } else {
+        covs3D_com = torch::empty({0, 6}, fopts);
+    }
+    return std::make_tuple(r.num_rendered, out_color, out_flow, out_depth, out_T, radii, geomBuffer, binningBuffer,
+                           imgBuffer, covs3D_com, out_means3D);
+}
+
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
+           torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
+RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Tensor& means3D,
+                               const torch::Tensor& out_means3D, const torch::Tensor& radii, const torch::Tensor& colors,
+                               const torch::Tensor& flows_2d, const torch::Tensor& opacities, const torch::Tensor& ts,
+                               const torch::Tensor& scales, const torch::Tensor& scales_t, const torch::Tensor& rotations,
+                               const torch::Tensor& rotations_r, const float scale_modifier,
+                               const torch::Tensor& cov3D_precomp, const float prefilter_var,
+                               const torch::Tensor& viewmatrix, const torch::Tensor& projmatrix, const float tan_fovx,
+                               const float tan_fovy, const torch::Tensor& dL_dout_color,
+                               const torch::Tensor& dL_dout_depth, const torch::Tensor& dL_dout_mask,
+                               const torch::Tensor& dL_dout_flow, const torch::Tensor& sh, const int degree,
+                               const int degree_t, const torch::Tensor& campos, const float timestamp,
+                               const float time_duration, const bool rot_4d, const int gaussian_dim,
+                               const bool force_sh_3d, const torch::Tensor& geomBuffer, const int R,
+                               const torch::Tensor& binningBuffer, const torch::Tensor& imageBuffer, const bool debug) {
+    TORCH_CHECK(means3D.is_cuda(), "means3D must be a CUDA tensor");
+    const c10::cuda::CUDAGuard guard(means3D.device());
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream().stream();
+    const int P = means3D.size(0);
+    const int H = dL_dout_color.size(1), W = dL_dout_color.size(2);
+    const int M = (sh.defined() && sh.numel() != 0) ? (int)sh.size(1) : 0;
+    auto opts = means3D.options().dtype(torch::kFloat32);
+
+    // accumulated by the blend kernel -> one zero-filled slab, sliced into the five API tensors
+    torch::Tensor slab = torch::zeros({(int64_t)P * 13}, opts);
+    torch::Tensor dL_dmeans2D = slab.narrow(0, 0, (int64_t)P * 3).view({P, 3});
+    torch::Tensor dL_dconic = slab.narrow(0, (int64_t)P * 3, (int64_t)P * 4).view({P, 2, 2});
+    torch::Tensor dL_dcolors = slab.narrow(0, (int64_t)P * 7, (int64_t)P * 3).view({P, 3});
+    torch::Tensor dL_dflows = slab.narrow(0, (int64_t)P * 10, (int64_t)P * 2).view({P, 2});
+    torch::Tensor dL_dopacity = slab.narrow(0, (int64_t)P * 12, (int64_t)P).view({P, 1});
+    // fully overwritten by the backward-preprocess kernel
+    torch::Tensor dL_dmeans3D = torch::empty({P, 3}, opts);
+    torch::Tensor dL_dts = torch::empty({P, 1}, opts);
+    torch::Tensor dL_dcov3D = torch::empty({P, 6}, opts);
+    torch::Tensor dL_dsh = torch::empty({P, M, 3}, opts);
+    torch::Tensor dL_dscales = torch::empty({P, 3}, opts);
+    torch::Tensor dL_dscales_t = torch::empty({P, 1}, opts);
+    torch::Tensor dL_drotations = torch::empty({P, 4}, opts);
+    torch::Tensor dL_drotations_r = torch::empty({P, 4}, opts);
+
+    if (P != 0) {
+        const auto bg_c = contig(background), om_c = contig(out_means3D), rad_c = contig(radii), col_c = contig(colors),
+                   flow_c = contig(flows_2d), op_c = contig(opacities), ts_c = contig(ts), sc_c = contig(scales),
+                   sct_c = contig(scales_t), rot_c = contig(rotations), rotr_c = contig(rotations_r),
+                   cov_c = contig(cov3D_precomp), view_c = contig(viewmatrix), proj_c = contig(projmatrix),
+                   gc_c = contig(dL_dout_color), gd_c = contig(dL_dout_depth), gm_c = contig(dL_dout_mask),
+                   gf_c = contig(dL_dout_flow), sh_c = contig(sh), cam_c = contig(campos), geo_c = contig(geomBuffer),
+                   bin_c = contig(binningBuffer), img_c = contig(imageBuffer);
+        fdgs_backward_args a;
+        memset(&a, 0, sizeof(a));
+        a.P = P; a.D = degree; a.D_t = degree_t; a.M = M; a.R = R;
+        a.background = fptr(bg_c); a.width = W; a.height = H;
+        a.out_means3D = fptr(om_c); a.shs = fptr(sh_c); a.colors_precomp = fptr(col_c); a.flows_2d = fptr(flow_c);
+        a.opacities = fptr(op_c); a.ts = fptr(ts_c); a.scales = fptr(sc_c); a.scales_t = fptr(sct_c);
+        a.scale_modifier = scale_modifier; a.rotations = fptr(rot_c); a.rotations_r = fptr(rotr_c);
+        a.cov3D_precomp = fptr(cov_c); a.prefilter_var = prefilter_var;
+        a.viewmatrix = fptr(view_c); a.projmatrix = fptr(proj_c); a.campos = fptr(cam_c);
+        a.timestamp = timestamp; a.time_duration = time_duration; a.rot_4d = rot_4d; a.gaussian_dim = gaussian_dim;
+        a.force_sh_3d = force_sh_3d; a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy;
+        a.radii = rad_c.data_ptr<int>();
+        a.geom_buffer = reinterpret_cast<const char*>(geo_c.data_ptr());
+        a.binning_buffer = bin_c.numel() ? reinterpret_cast<const char*>(bin_c.data_ptr()) : nullptr;
+        a.image_buffer = reinterpret_cast<const char*>(img_c.data_ptr());
+        a.dL_dpix = fptr(gc_c); a.dL_depths = fptr(gd_c); a.dL_masks = fptr(gm_c); a.dL_dpix_flow = fptr(gf_c);
+        a.debug = debug;
+        a.dL_dmean2D = dL_dmeans2D.data_ptr<float>(); a.dL_dconic = dL_dconic.data_ptr<float>();
+        a.dL_dopacity = dL_dopacity.data_ptr<float>(); a.dL_dcolor = dL_dcolors.data_ptr<float>();
+        a.dL_dflows = dL_dflows.data_ptr<float>(); a.dL_dmean3D = dL_dmeans3D.data_ptr<float>();
+        a.dL_dcov3D = dL_dcov3D.data_ptr<float>(); a.dL_dsh = M > 0 ? dL_dsh.data_ptr<float>() : nullptr;
+        a.dL_dts = dL_dts.data_ptr<float>(); a.dL_dscale = dL_dscales.data_ptr<float>();
+        a.dL_dscale_t = dL_dscales_t.data_ptr<float>(); a.dL_drot = dL_drotations.data_ptr<float>();
+        a.dL_drot_r = dL_drotations_r.data_ptr<float>();
+        check(fdgs_backward(&a, (void*)stream), "backward");
+    }
+    return std::make_tuple(dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dflows, dL_dts,
+                           dL_dscales, dL_dscales_t, dL_drotations, dL_drotations_r);
+}
+
+torch::Tensor markVisible(torch::Tensor& means3D, torch::Tensor& viewmatrix, torch::Tensor& projmatrix) {
+    const int P = means3D.size(0);
+    torch::Tensor present = torch::full({P}, false, means3D.options().dtype(at::kBool));
+    if (P != 0) {
+        const c10::cuda::CUDAGuard guard(means3D.device());
+        cudaStream_t stream = c10::cuda::getCurrentCUDAStream().stream();
+        const auto m = means3D.contiguous(), v = viewmatrix.contiguous(), pr = projmatrix.contiguous();
+        check(fdgs_mark_visible(P, m.data_ptr<float>(), v.data_ptr<float>(), pr.data_ptr<float>(),
+                                reinterpret_cast<unsigned char*>(present.data_ptr<bool>()), (void*)stream),
+              "mark_visible");
+    }
+    return present;
+}
+
+// Test hooks: private forward state as plain tensors (parity tests compare them with the oracle).
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
+DebugExportGeom(const torch::Tensor& geomBuffer, const int P) {
+    const c10::cuda::CUDAGuard guard(geomBuffer.device());
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream().stream();
+    auto f = geomBuffer.options().dtype(torch::kFloat32);
+    torch::Tensor depths = torch::zeros({P}, f), means2D = torch::zeros({P, 2}, f), conic = torch::zeros({P, 4}, f),
+                  rgb = torch::zeros({P, 3}, f);
+    torch::Tensor clamped = torch::zeros({P}, geomBuffer.options().dtype(torch::kByte));
+    torch::Tensor tiles = torch::zeros({P}, geomBuffer.options().dtype(torch::kInt32));
+    if (P > 0)
+        check(fdgs_debug_export_geom(reinterpret_cast<const char*>(geomBuffer.data_ptr()), P, depths.data_ptr<float>(),
+                                     means2D.data_ptr<float>(), conic.data_ptr<float>(), rgb.data_ptr<float>(),
+                                     clamped.data_ptr<uint8_t>(), reinterpret_cast<unsigned int*>(tiles.data_ptr<int>()),
+                                     (void*)stream),
+              "debug_export_geom");
+    return std::make_tuple(depths, means2D, conic, rgb, clamped, tiles);
+}
+
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> DebugExportBinning(const torch::Tensor& binningBuffer,
+                                                                           const torch::Tensor& imgBuffer, const int R,
+                                                                           const int W, const int H) {
+    const c10::cuda::CUDAGuard guard(imgBuffer.device());
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream().stream();
+    auto i32 = imgBuffer.options().dtype(torch::kInt32);
+    const int tiles = ((W + 15) / 16) * ((H + 15) / 16);
+    torch::Tensor point_list = torch::zeros({R}, i32), ranges = torch::zeros({tiles, 2}, i32),
+                  n_contrib = torch::zeros({H, W}, i32);
+    check(fdgs_debug_export_binning(R > 0 ? reinterpret_cast<const char*>(binningBuffer.data_ptr()) : nullptr,
+                                    reinterpret_cast<const char*>(imgBuffer.data_ptr()), R, W, H,
+                                    reinterpret_cast<unsigned int*>(point_list.data_ptr<int>()),
+                                    reinterpret_cast<unsigned int*>(ranges.data_ptr<int>()),
+                                    reinterpret_cast<unsigned int*>(n_contrib.data_ptr<int>()), (void*)stream),
+          "debug_export_binning");
+    return std::make_tuple(point_list, ranges, n_contrib);
+}
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+    m.def("rasterize_gaussians", &RasterizeGaussiansCUDA);
+    m.def("rasterize_gaussians_backward", &RasterizeGaussiansBackwardCUDA);
+    m.def("mark_visible", &markVisible);
+    m.def("debug_export_geom", &DebugExportGeom);
+    m.def("debug_export_binning", &DebugExportBinning);
+    m.def("fdgs_version", []() { return fdgs_version(); });
+}

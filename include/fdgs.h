@@ -1,0 +1,215 @@
+/*
+ * fdgs.h -- C-ABI of the B200-native differentiable 4D Gaussian rasterizer ("fdgs").
+ *
+ * This is the drop-in boundary of the hot path.  Every entry point replaces one
+ * method of the reference's L0 C++ API `CudaRasterizer::Rasterizer`
+ * (reference: diff-gaussian-rasterization/cuda_rasterizer/rasterizer.h:20-113):
+ *
+ *   fdgs_forward       <- Rasterizer::forward      (rasterizer.h:31-65,  rasterizer_impl.cu:199-364)
+ *   fdgs_backward      <- Rasterizer::backward     (rasterizer.h:67-112, rasterizer_impl.cu:368-496)
+ *   fdgs_mark_visible  <- Rasterizer::markVisible  (rasterizer.h:24-29,  rasterizer_impl.cu:142-154)
+ *
+ * Differences from the reference interface, all forced by "plain C, no C++ types":
+ *   - the three `std::function<char*(size_t)>` scratch allocators become a C
+ *     function pointer + opaque context (fdgs_alloc_fn);
+ *   - the ~40 positional arguments become two POD structs of raw device
+ *     pointers and scalars (field names = the reference's argument names);
+ *   - every call takes the CUDA stream to launch on (the reference uses the
+ *     legacy default stream implicitly) and returns an int status instead of
+ *     throwing; fdgs_last_error() gives the message for the calling thread.
+ *
+ * All pointers are DEVICE pointers unless stated otherwise.  Nullable inputs
+ * (colors_precomp, cov3D_precomp, shs, scales ...) follow the reference: NULL
+ * means "not provided" (reference: rasterize_points.cu:110-141 passes the
+ * data pointer of an empty tensor, i.e. NULL).
+ *
+ * The library never allocates or frees device memory itself; the three scratch
+ * buffers are obtained through the callbacks and are opaque to the caller
+ * (their layout is private and differs from the reference's GeometryState /
+ * BinningState / ImageState; they only have to be handed back unchanged to
+ * fdgs_backward, like the reference's geomBuffer/binningBuffer/imgBuffer).
+ */
+#ifndef FDGS_H_INCLUDED
+#define FDGS_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDGS_VERSION 1
+
+/* status codes */
+#define FDGS_OK 0
+#define FDGS_ERR_INVALID_ARG 1
+#define FDGS_ERR_CUDA 2
+#define FDGS_ERR_ALLOC 3
+#define FDGS_ERR_UNSUPPORTED 4
+
+/* Scratch allocator callback: must return a device pointer to at least
+ * `bytes` bytes (128-byte aligned or better), or NULL on failure.
+ * Replaces std::function<char*(size_t)> (reference: rasterizer.h:32-34,
+ * rasterize_points.cu:28-34 `resizeFunctional`). */
+typedef char* (*fdgs_alloc_fn)(void* ctx, size_t bytes);
+
+/* Inputs/outputs of one forward pass.  Field names follow
+ * Rasterizer::forward (reference: rasterizer.h:31-65). */
+typedef struct fdgs_forward_args {
+    int P;                 /* number of Gaussians                              */
+    int D;                 /* active spatial SH degree (0..3)                  */
+    int D_t;               /* active temporal SH degree (0..2)                 */
+    int M;                 /* SH coefficients per Gaussian (row length / 3)    */
+    const float* background;      /* [3]                                       */
+    int width, height;
+    const float* means3D;         /* [P,3]                                     */
+    const float* shs;             /* [P,M,3] or NULL                           */
+    const float* colors_precomp;  /* [P,3] or NULL                             */
+    const float* flows_precomp;   /* [P,2]                                     */
+    const float* opacities;       /* [P]                                       */
+    const float* ts;              /* [P] or NULL                               */
+    const float* scales;          /* [P,3] or NULL                             */
+    const float* scales_t;        /* [P] or NULL                               */
+    float scale_modifier;
+    const float* rotations;       /* [P,4] or NULL                             */
+    const float* rotations_r;     /* [P,4] or NULL                             */
+    const float* cov3D_precomp;   /* [P,6] or NULL                             */
+    float prefilter_var;
+    const float* viewmatrix;      /* [16], column-major (transposed torch)     */
+    const float* projmatrix;      /* [16], column-major                        */
+    const float* cam_pos;         /* [3]                                       */
+    float timestamp;
+    float time_duration;
+    int rot_4d;
+    int gaussian_dim;
+    int force_sh_3d;
+    float tan_fovx, tan_fovy;
+    int prefiltered;
+    int debug;             /* !=0: synchronise + check after every stage       */
+    /* outputs */
+    float* out_means3D;    /* [P,3]  written for every Gaussian (shifted mean) */
+    float* out_color;      /* [3,H,W]                                          */
+    float* out_flow;       /* [2,H,W]                                          */
+    float* out_depth;      /* [1,H,W]                                          */
+    float* out_T;          /* [1,H,W] final transmittance                      */
+    int* radii;            /* [P]                                              */
+} fdgs_forward_args;
+
+/* Scratch handles returned by fdgs_forward (device pointers obtained through
+ * the callbacks) plus what the torch shim needs to build `covs3D_com`. */
+typedef struct fdgs_forward_result {
+    int num_rendered;      /* R = number of (tile, Gaussian) instances         */
+    char* geom_buffer;
+    char* binning_buffer;
+    char* image_buffer;
+    size_t geom_bytes, binning_bytes, image_bytes;
+    const float* cov3D;    /* [P,6] inside geom_buffer (reference: rasterize_points.cu:144-147) */
+} fdgs_forward_result;
+
+/* Inputs/outputs of one backward pass.  Field names follow
+ * Rasterizer::backward (reference: rasterizer.h:67-112). */
+typedef struct fdgs_backward_args {
+    int P, D, D_t, M, R;
+    const float* background;
+    int width, height;
+    const float* out_means3D;     /* shifted means written by the forward      */
+    const float* shs;
+    const float* colors_precomp;
+    const float* flows_2d;
+    const float* opacities;
+    const float* ts;
+    const float* scales;
+    const float* scales_t;
+    float scale_modifier;
+    const float* rotations;
+    const float* rotations_r;
+    const float* cov3D_precomp;
+    float prefilter_var;
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* campos;
+    float timestamp;
+    float time_duration;
+    int rot_4d;
+    int gaussian_dim;
+    int force_sh_3d;
+    float tan_fovx, tan_fovy;
+    const int* radii;
+    const char* geom_buffer;
+    const char* binning_buffer;
+    const char* image_buffer;
+    const float* dL_dpix;         /* [3,H,W]                                   */
+    const float* dL_depths;       /* [1,H,W]                                   */
+    const float* dL_masks;        /* [1,H,W] grad of alpha = 1 - T             */
+    const float* dL_dpix_flow;    /* [2,H,W]                                   */
+    int debug;
+    /* Outputs.  The five "blend" gradients must be ZERO on entry (they are
+     * accumulated into, like the reference: rasterize_points.cu:201-213); the
+     * others are fully overwritten for every Gaussian (zeros where a Gaussian
+     * was not rendered), so they may be uninitialised on entry. */
+    float* dL_dmean2D;     /* [P,3]   accumulated                              */
+    float* dL_dconic;      /* [P,2,2] accumulated (x, y, -, w)                 */
+    float* dL_dopacity;    /* [P]     accumulated, then scaled by marginal_t   */
+    float* dL_dcolor;      /* [P,3]   accumulated                              */
+    float* dL_dflows;      /* [P,2]   accumulated                              */
+    float* dL_dmean3D;     /* [P,3]   overwritten                              */
+    float* dL_dcov3D;      /* [P,6]   overwritten                              */
+    float* dL_dsh;         /* [P,M,3] overwritten                              */
+    float* dL_dts;         /* [P]     overwritten                              */
+    float* dL_dscale;      /* [P,3]   overwritten                              */
+    float* dL_dscale_t;    /* [P]     overwritten                              */
+    float* dL_drot;        /* [P,4]   overwritten                              */
+    float* dL_drot_r;      /* [P,4]   overwritten                              */
+} fdgs_backward_args;
+
+/* Library / build identification. */
+int fdgs_version(void);
+/* Message of the last error on the calling thread ("" if none). */
+const char* fdgs_last_error(void);
+
+/* Sizes of the private scratch buffers (bytes), for callers that want to
+ * pre-allocate (reference: required<GeometryState>(P) etc.,
+ * rasterizer_impl.h:67-73). */
+size_t fdgs_geom_bytes(int P);
+size_t fdgs_image_bytes(int width, int height);
+size_t fdgs_binning_bytes(int num_rendered, int width, int height);
+
+/* Forward.  `stream` is a cudaStream_t passed as void*.  Performs exactly one
+ * host synchronisation on `stream` (to learn num_rendered and size the binning
+ * buffer), like the reference (rasterizer_impl.cu:302). */
+int fdgs_forward(const fdgs_forward_args* args,
+                 fdgs_alloc_fn geom_alloc, void* geom_ctx,
+                 fdgs_alloc_fn binning_alloc, void* binning_ctx,
+                 fdgs_alloc_fn image_alloc, void* image_ctx,
+                 void* stream,
+                 fdgs_forward_result* result);
+
+/* Backward.  Fully asynchronous on `stream`. */
+int fdgs_backward(const fdgs_backward_args* args, void* stream);
+
+/* present[i] = (view-space z of means3D[i] > 0.2)
+ * (reference: rasterizer_impl.cu:54-67, auxiliary.h:140-163). */
+int fdgs_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                      const float* projmatrix, unsigned char* present, void* stream);
+
+/* Test/diagnostic hooks (used by tests/ and bench.py only): copy private
+ * per-Gaussian / per-instance state out of the scratch buffers into plain
+ * caller-provided device arrays so that parity tests can compare them with the
+ * oracle bit for bit.  Any output pointer may be NULL. */
+int fdgs_debug_export_geom(const char* geom_buffer, int P,
+                           float* depths, float* means2D /*[P,2]*/,
+                           float* conic_opacity /*[P,4]*/, float* rgb /*[P,3]*/,
+                           unsigned char* clamped /*[P,3]*/, unsigned int* tiles_touched,
+                           void* stream);
+int fdgs_debug_export_binning(const char* binning_buffer, const char* image_buffer,
+                              int num_rendered, int width, int height,
+                              unsigned int* point_list /*[R]*/,
+                              unsigned int* ranges /*[tiles,2]*/,
+                              unsigned int* n_contrib /*[H*W]*/,
+                              void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDGS_H_INCLUDED */

@@ -1,0 +1,207 @@
+#!/usr/bin/env python3
+"""GPU bring-up / parity explorer (development tool, run under gpurun).
+
+For a list of synthetic configurations runs the compiled reference rasterizer (oracle/_ref) and
+the fdgs CUDA path on identical inputs and prints, field by field, how many elements differ
+bitwise and the max-norm relative error; then quick CUDA-event timings of both.
+Usage: python tools/first_light.py [--configs small,mid,cfg2,cfg3] [--golden DIR]
+"""
+import argparse
+import os
+import sys
+import time
+import traceback
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "4d-gaussian-splatting_b200"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import fdgs  # noqa: E402
+from fdgs import synth  # noqa: E402
+import oracle_py  # noqa: E402
+
+CONFIGS = {
+    "tiny": dict(P=2000, W=128, H=96, seed=11),
+    "small": dict(P=10000, W=256, H=256, seed=1235),
+    "flow": dict(P=20000, W=320, H=240, seed=77, flow=True, bg=(0.3, 0.6, 0.1)),
+    "negfov": dict(P=20000, W=320, H=240, seed=78, negative_fov=True, flow=True),
+    "mid": dict(P=100000, W=640, H=480, seed=1236),
+    "cfg2": dict(P=500000, W=1352, H=1014, seed=1236),
+    "cfg3": dict(P=2000000, W=1352, H=1014, seed=1237),
+}
+
+
+def fwd_args(st, sc, prefilter_var=-1.0):
+    e = torch.Tensor([])
+    return (st["bg"], sc.means3D, e, sc.flow_2d, sc.opacities, sc.ts, sc.scales, sc.scales_t, sc.rotations,
+            sc.rotations_r, st["scale_modifier"], e, prefilter_var, st["viewmatrix"], st["projmatrix"], st["tanfovx"],
+            st["tanfovy"], st["image_height"], st["image_width"], sc.shs, st["sh_degree"], st["sh_degree_t"],
+            st["campos"], st["timestamp"], st["time_duration"], st["rot_4d"], st["gaussian_dim"], st["force_sh_3d"],
+            st["prefiltered"], st["debug"])
+
+
+def bwd_args(st, sc, fw, grads, prefilter_var=-1.0):
+    e = torch.Tensor([])
+    (num_rendered, color, flow, depth, T, radii, geom, binning, img, covs, out_means3D) = fw
+    gc, gd, ga, gf = grads
+    return (st["bg"], sc.means3D, out_means3D, radii, e, sc.flow_2d, sc.opacities, sc.ts, sc.scales, sc.scales_t,
+            sc.rotations, sc.rotations_r, st["scale_modifier"], e, prefilter_var, st["viewmatrix"], st["projmatrix"],
+            st["tanfovx"], st["tanfovy"], gc, gd, ga, gf, sc.shs, st["sh_degree"], st["sh_degree_t"], st["campos"],
+            st["timestamp"], st["time_duration"], st["rot_4d"], st["gaussian_dim"], st["force_sh_3d"], geom,
+            num_rendered, binning, img, st["debug"])
+
+
+def bitdiff(a, b):
+    a = a.contiguous().view(-1)
+    b = b.contiguous().view(-1)
+    if a.dtype.is_floating_point:
+        return int((a.view(torch.int32) != b.view(torch.int32)).sum())
+    return int((a != b).sum())
+
+
+def relerr(a, b):
+    a = a.float()
+    b = b.float()
+    d = (a - b).abs().max().item()
+    n = b.abs().max().item()
+    return d / n if n > 0 else d
+
+
+GRAD_NAMES = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dflows", "dL_dts",
+              "dL_dscales", "dL_dscales_t", "dL_drot", "dL_drot_r"]
+
+
+def timeit(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
+def run_config(name, cfg, golden_dir=None):
+    print("=" * 100)
+    print("CONFIG", name, cfg, flush=True)
+    dev = torch.device("cuda:0")
+    cam = synth.make_camera(cfg["W"], cfg["H"], negative_fov=cfg.get("negative_fov", False))
+    sc_cpu = synth.make_scene(cfg["P"], cam, cfg["seed"], flow=cfg.get("flow", False))
+    sc = sc_cpu.to(dev)
+    bg = torch.tensor(cfg.get("bg", (0.0, 0.0, 0.0)), dtype=torch.float32)
+    st = synth.raster_settings(cam, sc_cpu, bg=bg, device=dev)
+    C = fdgs.ext()
+    ref = oracle_py.ref_module() if oracle_py.ref_available() else None
+    P, W, H = cfg["P"], cfg["W"], cfg["H"]
+    a = fwd_args(st, sc)
+    mine = C.rasterize_gaussians(*a)
+    torch.cuda.synchronize()
+    print("mine: num_rendered", mine[0], "visible", int((mine[5] > 0).sum()), flush=True)
+    g = torch.Generator().manual_seed(cfg["seed"] + 999)
+    gc = torch.randn(3, H, W, generator=g).to(dev)
+    gd = (0.1 * torch.randn(1, H, W, generator=g)).to(dev)
+    ga = (0.1 * torch.randn(1, H, W, generator=g)).to(dev)
+    gf = (0.1 * torch.randn(2, H, W, generator=g)).to(dev)
+    grads = (gc, gd, ga, gf)
+    mine_b = C.rasterize_gaussians_backward(*bwd_args(st, sc, mine, grads))
+    torch.cuda.synchronize()
+    mg = C.debug_export_geom(mine[6], P)
+    mb = C.debug_export_binning(mine[7], mine[8], mine[0], W, H)
+    ncm = mb[2]
+    print("mine: mean n_contrib %.2f  mean T %.4f  color mean %.4f" % (ncm.float().mean().item(), mine[4].mean().item(),
+                                                                        mine[1].mean().item()), flush=True)
+    if ref is not None:
+        rf = ref.rasterize_gaussians(*a)
+        torch.cuda.synchronize()
+        rb = ref.rasterize_gaussians_backward(*bwd_args(st, sc, rf, grads))
+        torch.cuda.synchronize()
+        print("ref : num_rendered", rf[0], "visible", int((rf[5] > 0).sum()))
+        vis = rf[5] > 0
+        rg = oracle_py.ref_geom_views(rf[6], P)
+        print("-- per-Gaussian (over reference-visible rows unless noted): #bitwise-different / maxrel")
+        print("radii            diff=%d" % bitdiff(mine[5], rf[5]))
+        print("tiles_touched    diff=%d" % bitdiff(mg[5], rg["tiles_touched"]))
+        print("out_means3D      diff=%d (all rows)" % bitdiff(mine[10], rf[10]))
+        for nm, m_, r_ in (("depths", mg[0], rg["depths"]), ("means2D", mg[1], rg["means2D"]),
+                           ("conic_opacity", mg[2], rg["conic_opacity"]), ("rgb", mg[3], rg["rgb"]),
+                           ("cov3D", mine[9], rf[9])):
+            print("%-16s diff=%d  maxrel=%.3e" % (nm, bitdiff(m_[vis], r_[vis]), relerr(m_[vis], r_[vis])))
+        mclamp = torch.stack([(mg[4] >> i) & 1 for i in range(3)], 1)
+        print("clamped          diff=%d" % int((mclamp[vis] != rg["clamped"][vis]).sum()))
+        if mine[0] == rf[0] and rf[0] > 0:
+            rpl = oracle_py.ref_binning_point_list(rf[7], rf[0])
+            print("point_list       diff=%d of %d" % (bitdiff(mb[0], rpl), rf[0]))
+            ri = oracle_py.ref_image_views(rf[8], W * H)
+            print("n_contrib        diff=%d" % bitdiff(ncm.view(-1), ri["n_contrib"]))
+            nt = ((W + 15) // 16) * ((H + 15) // 16)
+            print("ranges           diff=%d" % bitdiff(mb[1], ri["ranges"][:nt]))
+        print("-- images: #bitwise-different / maxrel")
+        for nm, i in (("color", 1), ("flow", 2), ("depth", 3), ("T", 4)):
+            print("%-16s diff=%d  maxrel=%.3e" % (nm, bitdiff(mine[i], rf[i]), relerr(mine[i], rf[i])))
+        rb2 = ref.rasterize_gaussians_backward(*bwd_args(st, sc, rf, grads))
+        print("-- gradients: maxrel(mine vs ref)   [reference self-noise run-to-run]")
+        for nm, m_, r_, r2 in zip(GRAD_NAMES, mine_b, rb, rb2):
+            if r_.numel() == 0:
+                continue
+            print("%-16s %.3e   [%.3e]   max|ref|=%.3e" % (nm, relerr(m_, r_), relerr(r2, r_), r_.abs().max().item()))
+    else:
+        print("(reference module not available)")
+
+    if golden_dir and ref is not None and P <= 20000:
+        os.makedirs(golden_dir, exist_ok=True)
+        rpl = oracle_py.ref_binning_point_list(rf[7], rf[0]) if rf[0] > 0 else torch.zeros(0, dtype=torch.int32)
+        ri = oracle_py.ref_image_views(rf[8], W * H)
+        nt = ((W + 15) // 16) * ((H + 15) // 16)
+        np.savez_compressed(
+            os.path.join(golden_dir, "golden_%s.npz" % name),
+            cfg=np.array(repr(cfg)), num_rendered=np.int64(rf[0]), color=rf[1].cpu().numpy(), flow=rf[2].cpu().numpy(),
+            depth=rf[3].cpu().numpy(), T=rf[4].cpu().numpy(), radii=rf[5].cpu().numpy(),
+            covs3D=rf[9].cpu().numpy(), out_means3D=rf[10].cpu().numpy(),
+            depths=rg["depths"].cpu().numpy(), means2D=rg["means2D"].cpu().numpy(),
+            conic_opacity=rg["conic_opacity"].cpu().numpy(), rgb=rg["rgb"].cpu().numpy(),
+            clamped=rg["clamped"].cpu().numpy(), tiles_touched=rg["tiles_touched"].cpu().numpy(),
+            point_list=rpl.cpu().numpy(), n_contrib=ri["n_contrib"].cpu().numpy(),
+            ranges=ri["ranges"][:nt].cpu().numpy(),
+            **{("grad_" + n): t.cpu().numpy() for n, t in zip(GRAD_NAMES, rb)})
+        print("golden written", flush=True)
+
+    # timings
+    try:
+        t_mf = timeit(lambda: C.rasterize_gaussians(*a))
+        t_mb = timeit(lambda: C.rasterize_gaussians_backward(*bwd_args(st, sc, mine, grads)))
+        line = "TIMING %s mine fwd %.3f ms bwd %.3f ms" % (name, t_mf, t_mb)
+        if ref is not None:
+            t_rf = timeit(lambda: ref.rasterize_gaussians(*a))
+            t_rb = timeit(lambda: ref.rasterize_gaussians_backward(*bwd_args(st, sc, rf, grads)))
+            line += " | ref fwd %.3f ms bwd %.3f ms | speedup fwd %.2fx bwd %.2fx total %.2fx" % (
+                t_rf, t_rb, t_rf / t_mf, t_rb / t_mb, (t_rf + t_rb) / (t_mf + t_mb))
+        print(line, flush=True)
+    except Exception:
+        traceback.print_exc()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="tiny,small,flow,negfov,mid,cfg2,cfg3")
+    ap.add_argument("--golden", default=None)
+    args = ap.parse_args()
+    print(torch.cuda.get_device_name(0), torch.version.cuda, flush=True)
+    for name in args.configs.split(","):
+        try:
+            run_config(name, CONFIGS[name], args.golden)
+        except Exception:
+            traceback.print_exc()
+            torch.cuda.synchronize()
+        sys.stdout.flush()
+
+
+if __name__ == "__main__":
+    main()
