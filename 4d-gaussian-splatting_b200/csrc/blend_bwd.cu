@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(BB_THREADS) blend_bwd_kernel(const BlendBwdPar
                     const float dx = fsub(q0.x, pxf);
                     const float dy = fsub(q0.y, pyf);
                     const float power =
-                        fsub(fmul(ffma(dx, fmul(dx, q1.x), fmul(dy, fmul(dy, q1.z))), -0.5f), fmul(dy, fmul(dx, q1.y)));
+                        ffma(ffma(dx, fmul(dx, q1.x), fmul(dy, fmul(dy, q1.z))), -0.5f, -fmul(dy, fmul(dx, q1.y)));
                     bool contrib = (pos < my_last) && !(power > 0.0f) && !(power < q0.z);
                     float G = 0.f, alpha = 0.f;
                     if (contrib) {

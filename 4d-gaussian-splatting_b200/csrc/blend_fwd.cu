@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(BF_THREADS) blend_fwd_kernel(const BlendFwdPar
                     const float dx = fsub(q0.x, pxf);
                     const float dy = fsub(q0.y, pyf);
                     const float power =
-                        fsub(fmul(ffma(dx, fmul(dx, q1.x), fmul(dy, fmul(dy, q1.z))), -0.5f), fmul(dy, fmul(dx, q1.y)));
+                        ffma(ffma(dx, fmul(dx, q1.x), fmul(dy, fmul(dy, q1.z))), -0.5f, -fmul(dy, fmul(dx, q1.y)));
                     if (done || power > 0.0f || power < q0.z) continue;
                     const float alpha = fminf(fmul(q1.w, expf(power)), 0.99f);
                     if (alpha < 1.0f / 255.0f) continue;

@@ -66,21 +66,35 @@ __device__ __forceinline__ void build_M4(float sx, float sy, float sz, float st,
                                          float (*Rout)[4] = nullptr) {
     const float a = rot.x, b = rot.y, c = rot.z, d = rot.w;
     const float p = rot_r.x, q = rot_r.y, r = rot_r.z, s = rot_r.w;
-    // glm column-major constructors, forward.cu:315-327
-    const float Ml[4][4] = {{a, b, -c, d}, {-b, a, d, c}, {c, -d, a, b}, {-d, -c, -b, a}};
-    const float Mr[4][4] = {{p, q, -r, -s}, {-q, p, s, -r}, {r, -s, p, -q}, {s, r, q, p}};
+    // R = M_r * M_l with M_l = (a,b,-c,d | -b,a,d,c | c,-d,a,b | -d,-c,-b,a) and
+    // M_r = (p,q,-r,-s | -q,p,s,-r | r,-s,p,-q | s,r,q,p) (glm column-major, forward.cu:315-329).
+    // Each entry is a signed sum of four products; which products are fused into FFMAs is what
+    // ptxas decided for the reference kernel (read from its SASS with tools/sass2expr.py) -- it
+    // differs from entry to entry because the 16 products a*p .. d*s are shared between entries.
+    float R[4][4];
+    R[0][0] = ffma(d, s, fadd(ffma(a, p, -fmul(b, q)), -fmul(c, r)));
+    R[0][1] = ffma(d, r, ffma(c, s, ffma(a, q, fmul(b, p))));
+    R[0][2] = fadd(ffma(-c, p, ffma(b, s, -fmul(a, r))), fmul(d, q));
+    R[0][3] = ffma(d, p, ffma(c, q, ffma(b, -r, -fmul(a, s))));
+    R[1][0] = ffma(c, s, ffma(d, r, ffma(a, -q, -fmul(b, p))));
+    R[1][1] = fadd(fmul(c, r), ffma(-d, s, ffma(a, p, -fmul(b, q))));
+    R[1][2] = ffma(c, q, ffma(d, p, ffma(b, r, fmul(a, s))));
+    R[1][3] = ffma(c, p, fadd(ffma(b, s, -fmul(a, r)), -fmul(d, q)));
+    R[2][0] = ffma(b, s, fadd(fmul(a, r), ffma(c, p, fmul(d, q))));
+    R[2][1] = ffma(b, r, fadd(-fmul(a, s), ffma(c, q, -fmul(d, p))));
+    R[2][2] = fadd(fmul(b, q), ffma(a, p, ffma(-d, s, -fmul(c, r))));
+    R[2][3] = fadd(fmul(b, p), ffma(-a, q, ffma(d, r, -fmul(c, s))));
+    R[3][0] = fadd(fmul(a, s), ffma(-b, r, ffma(c, q, -fmul(d, p))));
+    R[3][1] = fadd(fmul(a, r), ffma(b, s, ffma(-c, p, -fmul(d, q))));
+    R[3][2] = ffma(a, q, fadd(-fmul(b, p), ffma(d, r, -fmul(c, s))));
+    R[3][3] = ffma(a, p, fadd(fmul(b, q), ffma(d, s, fmul(c, r))));
     const float sc[4] = {sx, sy, sz, st};
 #pragma unroll
     for (int col = 0; col < 4; ++col) {
 #pragma unroll
         for (int row = 0; row < 4; ++row) {
-            // R = M_r * M_l (glm mat4*mat4, type_mat4x4.inl:630-648): plain products, left-assoc sum
-            float t = fmul(Mr[0][row], Ml[col][0]);
-            t = fadd(t, fmul(Mr[1][row], Ml[col][1]));
-            t = fadd(t, fmul(Mr[2][row], Ml[col][2]));
-            t = fadd(t, fmul(Mr[3][row], Ml[col][3]));
-            if (WANT_R) Rout[col][row] = t;
-            M[col][row] = fmul(sc[row], t);   // M = S * R, S diagonal
+            if (WANT_R) Rout[col][row] = R[col][row];
+            M[col][row] = fmul(sc[row], R[col][row]);   // M = S * R, S diagonal
         }
     }
 }
@@ -114,22 +128,22 @@ __device__ __forceinline__ float marginal_from(float dt, float cov_t, float pref
 // reference: forward.cu:242-276 computeCov3D (quaternion NOT normalised, :251)
 __device__ __forceinline__ void build_M3(float sx, float sy, float sz, const float4 q, float M[3][3]) {
     const float r = q.x, x = q.y, y = q.z, z = q.w;
+    // fusion pattern as in the reference kernel's SASS (tools/sass2expr.py)
     const float yy = fmul(y, y), zz = fmul(z, z);
-    const float xy = fmul(x, y), rz = fmul(r, z), xz = fmul(x, z), ry = fmul(r, y);
-    const float yz = fmul(y, z), rx = fmul(r, x);
+    const float rz = fmul(r, z), xz = fmul(x, z), rx = fmul(r, x);
     const float A = fadd(yy, zz);
     const float B = ffma(x, x, zz);
     const float C = ffma(x, x, yy);
     float R[3][3];
     float t;
     R[0][0] = fsub(1.f, fadd(A, A));
-    t = fsub(xy, rz); R[0][1] = fadd(t, t);
-    t = fadd(xz, ry); R[0][2] = fadd(t, t);
-    t = fadd(xy, rz); R[1][0] = fadd(t, t);
+    t = ffma(x, y, -rz); R[0][1] = fadd(t, t);
+    t = ffma(r, y, xz);  R[0][2] = fadd(t, t);
+    t = ffma(x, y, rz);  R[1][0] = fadd(t, t);
     R[1][1] = fsub(1.f, fadd(B, B));
-    t = fsub(yz, rx); R[1][2] = fadd(t, t);
-    t = fsub(xz, ry); R[2][0] = fadd(t, t);
-    t = fadd(yz, rx); R[2][1] = fadd(t, t);
+    t = ffma(y, z, -rx); R[1][2] = fadd(t, t);
+    t = ffma(-r, y, xz); R[2][0] = fadd(t, t);
+    t = ffma(y, z, rx);  R[2][1] = fadd(t, t);
     R[2][2] = fsub(1.f, fadd(C, C));
     const float sc[3] = {sx, sy, sz};
 #pragma unroll

@@ -27,6 +27,20 @@ struct ShBasis {
     float l[16];   // l0m0, l1m1, l1m0, l1p1, l2m2 .. l3p3
 };
 
+// degree-3 basis, shared by the 3D and 4D variants (reference: forward.cu:53-59 / :125-131); the
+// polynomial factors are fused as in the reference kernel's SASS (3*xx - yy -> fma(xx,3,-yy) ...)
+__device__ __forceinline__ void sh_basis_l3(float x, float y, float z, float xx, float yy, float zz, float xy,
+                                            float l[16]) {
+    const float four_zz_xx_yy = fadd(-yy, ffma(zz, 4.f, -xx));   // 4zz - xx - yy
+    l[9] = fmul(fmul(y, kSH_C3[0]), ffma(xx, 3.f, -yy));
+    l[10] = fmul(fmul(xy, kSH_C3[1]), z);
+    l[11] = fmul(fmul(y, kSH_C3[2]), four_zz_xx_yy);
+    l[12] = fmul(fmul(z, kSH_C3[3]), ffma(yy, -3.f, ffma(xx, -3.f, fadd(zz, zz))));
+    l[13] = fmul(four_zz_xx_yy, fmul(x, kSH_C3[4]));
+    l[14] = fmul(fsub(xx, yy), fmul(z, kSH_C3[5]));
+    l[15] = fmul(fmul(x, kSH_C3[6]), ffma(yy, -3.f, xx));
+}
+
 // reference: forward.cu:79-131 (4D variant; the double-promoted l2m0 and integer literals)
 __device__ __forceinline__ void sh_basis_4d(float x, float y, float z, int deg, ShBasis& B) {
     B.l[0] = kSH_C0;
@@ -43,15 +57,7 @@ __device__ __forceinline__ void sh_basis_4d(float x, float y, float z, int deg, 
             B.l[6] = (float)(((((double)zz + (double)zz) - (double)xx) - (double)yy) * (double)kSH_C2[2]);
             B.l[7] = fmul(xz, kSH_C2[3]);
             B.l[8] = fmul(fsub(xx, yy), kSH_C2[4]);
-            if (deg > 2) {
-                B.l[9] = fmul(fmul(y, kSH_C3[0]), fsub(fmul(xx, 3.f), yy));
-                B.l[10] = fmul(z, fmul(xy, kSH_C3[1]));
-                B.l[11] = fmul(fmul(y, kSH_C3[2]), fsub(fsub(fmul(zz, 4.f), xx), yy));
-                B.l[12] = fmul(fmul(z, kSH_C3[3]), fsub(fsub(fadd(zz, zz), fmul(xx, 3.f)), fmul(yy, 3.f)));
-                B.l[13] = fmul(fmul(x, kSH_C3[4]), fsub(fsub(fmul(zz, 4.f), xx), yy));
-                B.l[14] = fmul(fmul(z, kSH_C3[5]), fsub(xx, yy));
-                B.l[15] = fmul(fmul(x, kSH_C3[6]), fsub(xx, fmul(yy, 3.f)));
-            }
+            if (deg > 2) sh_basis_l3(x, y, z, xx, yy, zz, xy, B.l);
         }
     }
 }
@@ -141,14 +147,16 @@ __device__ __forceinline__ void sh_color_3d(const Row& row, int M, int deg, floa
     row.load_block(0, M, v);
     const float xx = fmul(x, x), yy = fmul(y, y), zz = fmul(z, z);
     const float xy = fmul(x, y), yz = fmul(y, z), xz = fmul(x, z);
+    float l3[16];
+    if (deg > 2) sh_basis_l3(x, y, z, xx, yy, zz, xy, l3);
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         float r = fmul(v[ch], kSH_C0);
         if (deg > 0) {
-            // result - C1*y*sh1 + C1*z*sh2 - C1*x*sh3
-            r = fsub(r, fmul(fmul(y, kSH_C1), v[3 + ch]));
+            // result - C1*y*sh1 + C1*z*sh2 - C1*x*sh3 ... : one FFMA chain in the reference's SASS
+            r = ffma(-fmul(y, kSH_C1), v[3 + ch], r);
             r = ffma(fmul(z, kSH_C1), v[6 + ch], r);
-            r = fsub(r, fmul(fmul(x, kSH_C1), v[9 + ch]));
+            r = ffma(-fmul(x, kSH_C1), v[9 + ch], r);
             if (deg > 1) {
                 r = ffma(fmul(xy, kSH_C2[0]), v[12 + ch], r);
                 r = ffma(fmul(yz, kSH_C2[1]), v[15 + ch], r);
@@ -156,14 +164,8 @@ __device__ __forceinline__ void sh_color_3d(const Row& row, int M, int deg, floa
                 r = ffma(fmul(xz, kSH_C2[3]), v[21 + ch], r);
                 r = ffma(fmul(fsub(xx, yy), kSH_C2[4]), v[24 + ch], r);
                 if (deg > 2) {
-                    r = ffma(fmul(fmul(y, kSH_C3[0]), fsub(fmul(xx, 3.f), yy)), v[27 + ch], r);
-                    r = ffma(fmul(z, fmul(xy, kSH_C3[1])), v[30 + ch], r);
-                    r = ffma(fmul(fmul(y, kSH_C3[2]), fsub(fsub(fmul(zz, 4.f), xx), yy)), v[33 + ch], r);
-                    r = ffma(fmul(fmul(z, kSH_C3[3]), fsub(fsub(fadd(zz, zz), fmul(xx, 3.f)), fmul(yy, 3.f))),
-                             v[36 + ch], r);
-                    r = ffma(fmul(fmul(x, kSH_C3[4]), fsub(fsub(fmul(zz, 4.f), xx), yy)), v[39 + ch], r);
-                    r = ffma(fmul(fmul(z, kSH_C3[5]), fsub(xx, yy)), v[42 + ch], r);
-                    r = ffma(fmul(fmul(x, kSH_C3[6]), fsub(xx, fmul(yy, 3.f))), v[45 + ch], r);
+#pragma unroll
+                    for (int k = 9; k < 16; ++k) r = ffma(l3[k], v[3 * k + ch], r);
                 }
             }
         }
@@ -279,8 +281,8 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const Prepr
                 cov2d_from_T(Pj, c3, ca, cb, cc);
                 ca = fadd(ca, 0.3f);
                 cc = fadd(cc, 0.3f);
-                const float bb = fmul(cb, cb);
-                const float det = fsub(fmul(ca, cc), bb);
+                // cov.x*cov.z - cov.y*cov.y: ptxas fuses the first product (SASS of the reference)
+                const float det = ffma(ca, cc, -fmul(cb, cb));
                 if (det == 0.0f) {
                     alive = false;
                 } else {
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const Prepr
                     cony = fmul(det_inv, -cb);
                     conz = fmul(ca, det_inv);
                     const float mid = fmul(fadd(ca, cc), 0.5f);
-                    const float sq = fsqrt(fmaxf(fsub(fmul(mid, mid), det), 0.1f));
+                    const float sq = fsqrt(fmaxf(ffma(mid, mid, -det), 0.1f));
                     const float lam = fmaxf(fadd(mid, sq), fsub(mid, sq));
                     const float my_radius = ceilf(fmul(fsqrt(lam), 3.f));
                     px = ndc2pix(projx, a.W);

@@ -129,36 +129,47 @@ static float marginal_of(float dt, float var, float prefilter_var) {
 static void build_M4(const float sc[4], const float* rot, const float* rot_r, float M[4][4], float R[4][4]) {
     const float a = rot[0], b = rot[1], c = rot[2], d = rot[3];
     const float p = rot_r[0], q = rot_r[1], r = rot_r[2], s = rot_r[3];
-    const float Ml[4][4] = {{a, b, -c, d}, {-b, a, d, c}, {c, -d, a, b}, {-d, -c, -b, a}};
-    const float Mr[4][4] = {{p, q, -r, -s}, {-q, p, s, -r}, {r, -s, p, -q}, {s, r, q, p}};
+    /* R = M_r * M_l, M_l = (a,b,-c,d | -b,a,d,c | c,-d,a,b | -d,-c,-b,a),
+     * M_r = (p,q,-r,-s | -q,p,s,-r | r,-s,p,-q | s,r,q,p)  (glm columns, forward.cu:315-329).
+     * Mathematically R[c][r] = sum_k M_r[k][r]*M_l[c][k]; the rounding sequence below (which of
+     * the shared products a*p..d*s end up inside an FFMA) is the one in the reference kernel's
+     * machine code, entry by entry. */
+    R[0][0] = ffma(d, s, fadd(ffma(a, p, -fmul(b, q)), -fmul(c, r)));
+    R[0][1] = ffma(d, r, ffma(c, s, ffma(a, q, fmul(b, p))));
+    R[0][2] = fadd(ffma(-c, p, ffma(b, s, -fmul(a, r))), fmul(d, q));
+    R[0][3] = ffma(d, p, ffma(c, q, ffma(b, -r, -fmul(a, s))));
+    R[1][0] = ffma(c, s, ffma(d, r, ffma(a, -q, -fmul(b, p))));
+    R[1][1] = fadd(fmul(c, r), ffma(-d, s, ffma(a, p, -fmul(b, q))));
+    R[1][2] = ffma(c, q, ffma(d, p, ffma(b, r, fmul(a, s))));
+    R[1][3] = ffma(c, p, fadd(ffma(b, s, -fmul(a, r)), -fmul(d, q)));
+    R[2][0] = ffma(b, s, fadd(fmul(a, r), ffma(c, p, fmul(d, q))));
+    R[2][1] = ffma(b, r, fadd(-fmul(a, s), ffma(c, q, -fmul(d, p))));
+    R[2][2] = fadd(fmul(b, q), ffma(a, p, ffma(-d, s, -fmul(c, r))));
+    R[2][3] = fadd(fmul(b, p), ffma(-a, q, ffma(d, r, -fmul(c, s))));
+    R[3][0] = fadd(fmul(a, s), ffma(-b, r, ffma(c, q, -fmul(d, p))));
+    R[3][1] = fadd(fmul(a, r), ffma(b, s, ffma(-c, p, -fmul(d, q))));
+    R[3][2] = ffma(a, q, fadd(-fmul(b, p), ffma(d, r, -fmul(c, s))));
+    R[3][3] = ffma(a, p, fadd(fmul(b, q), ffma(d, s, fmul(c, r))));
     for (int col = 0; col < 4; ++col)
-        for (int row = 0; row < 4; ++row) {
-            /* glm mat4*mat4 (type_mat4x4.inl:630-648): products rounded separately, summed left to right */
-            float t = fmul(Mr[0][row], Ml[col][0]);
-            t = fadd(t, fmul(Mr[1][row], Ml[col][1]));
-            t = fadd(t, fmul(Mr[2][row], Ml[col][2]));
-            t = fadd(t, fmul(Mr[3][row], Ml[col][3]));
-            R[col][row] = t;
-            M[col][row] = fmul(sc[row], t);
-        }
+        for (int row = 0; row < 4; ++row) M[col][row] = fmul(sc[row], R[col][row]);
 }
 static inline float coldot4(const float* A, const float* B) { return dot4(A[0], B[0], A[1], B[1], A[2], B[2], A[3], B[3]); }
 
 /* reference: forward.cu:242-276 */
 static void build_M3(const float sc[3], const float* q, float M[3][3], float R[3][3]) {
     const float r = q[0], x = q[1], y = q[2], z = q[3];
-    const float yy = fmul(y, y), zz = fmul(z, z), xy = fmul(x, y), rz = fmul(r, z), xz = fmul(x, z), ry = fmul(r, y);
-    const float yz = fmul(y, z), rx = fmul(r, x);
+    const float yy = fmul(y, y), zz = fmul(z, z), rz = fmul(r, z), xz = fmul(x, z), rx = fmul(r, x);
     const float A = fadd(yy, zz), B = ffma(x, x, zz), C = ffma(x, x, yy);
     float t;
+    /* 2*(x*y - r*z) etc.: the second product of each pair is fused in the reference's machine code */
     R[0][0] = fsub(1.f, fadd(A, A));
-    t = fsub(xy, rz); R[0][1] = fadd(t, t);
-    t = fadd(xz, ry); R[0][2] = fadd(t, t);
-    t = fadd(xy, rz); R[1][0] = fadd(t, t);
+    t = ffma(x, y, -rz); R[0][1] = fadd(t, t);
+    t = ffma(r, y, xz);  R[0][2] = fadd(t, t);
+    t = ffma(x, y, rz);  R[1][0] = fadd(t, t);
     R[1][1] = fsub(1.f, fadd(B, B));
-    t = fsub(yz, rx); R[1][2] = fadd(t, t);
-    t = fsub(xz, ry); R[2][0] = fadd(t, t);
-    t = fadd(yz, rx); R[2][1] = fadd(t, t);
+    t = ffma(y, z, -rx); R[1][2] = fadd(t, t);
+    t = ffma(-r, y, xz); R[2][0] = fadd(t, t);
+    t = ffma(y, z, rx);  R[2][1] = fadd(t, t);
     R[2][2] = fsub(1.f, fadd(C, C));
     for (int c = 0; c < 3; ++c)
         for (int rr = 0; rr < 3; ++rr) M[c][rr] = fmul(sc[rr], R[c][rr]);
@@ -204,31 +215,40 @@ static void cov2d(const ProjT* P, const float* c, float* a, float* b, float* cc)
 }
 
 /* ---- SH colour ---------------------------------------------------------------------------- */
-/* reference: forward.cu:20-71 computeColorFromSH; returns the value before "+0.5, clamp" */
+/* degree-3 basis l[9..15] (forward.cu:53-59 / :125-131).  "3*xx - yy" and friends are single
+ * FFMAs in the reference's machine code. */
+static void sh_l3(float x, float y, float z, float xx, float yy, float zz, float xy, float l[16]) {
+    const float w = fadd(-yy, ffma(zz, 4.f, -xx)); /* 4zz - xx - yy */
+    l[9] = fmul(fmul(y, SH_C3[0]), ffma(xx, 3.f, -yy));
+    l[10] = fmul(fmul(xy, SH_C3[1]), z);
+    l[11] = fmul(fmul(y, SH_C3[2]), w);
+    l[12] = fmul(fmul(z, SH_C3[3]), ffma(yy, -3.f, ffma(xx, -3.f, fadd(zz, zz))));
+    l[13] = fmul(w, fmul(x, SH_C3[4]));
+    l[14] = fmul(fsub(xx, yy), fmul(z, SH_C3[5]));
+    l[15] = fmul(fmul(x, SH_C3[6]), ffma(yy, -3.f, xx));
+}
+
+/* reference: forward.cu:20-71 computeColorFromSH; returns the value before "+0.5, clamp".
+ * The whole expression is one FFMA chain in the reference's machine code. */
 static void sh_color_3d(const float* sh, int deg, float x, float y, float z, float out[3]) {
     const float xx = fmul(x, x), yy = fmul(y, y), zz = fmul(z, z), xy = fmul(x, y), yz = fmul(y, z), xz = fmul(x, z);
+    float l[16];
+    if (deg > 2) sh_l3(x, y, z, xx, yy, zz, xy, l);
     for (int ch = 0; ch < 3; ++ch) {
 #define S(k) sh[3 * (k) + ch]
         float r = fmul(S(0), SH_C0);
         if (deg > 0) {
-            r = fsub(r, fmul(fmul(y, SH_C1), S(1)));
+            r = ffma(-fmul(y, SH_C1), S(1), r);
             r = ffma(fmul(z, SH_C1), S(2), r);
-            r = fsub(r, fmul(fmul(x, SH_C1), S(3)));
+            r = ffma(-fmul(x, SH_C1), S(3), r);
             if (deg > 1) {
                 r = ffma(fmul(xy, SH_C2[0]), S(4), r);
                 r = ffma(fmul(yz, SH_C2[1]), S(5), r);
                 r = ffma(fmul(fsub(fsub(fadd(zz, zz), xx), yy), SH_C2[2]), S(6), r);
                 r = ffma(fmul(xz, SH_C2[3]), S(7), r);
                 r = ffma(fmul(fsub(xx, yy), SH_C2[4]), S(8), r);
-                if (deg > 2) {
-                    r = ffma(fmul(fmul(y, SH_C3[0]), fsub(fmul(xx, 3.f), yy)), S(9), r);
-                    r = ffma(fmul(z, fmul(xy, SH_C3[1])), S(10), r);
-                    r = ffma(fmul(fmul(y, SH_C3[2]), fsub(fsub(fmul(zz, 4.f), xx), yy)), S(11), r);
-                    r = ffma(fmul(fmul(z, SH_C3[3]), fsub(fsub(fadd(zz, zz), fmul(xx, 3.f)), fmul(yy, 3.f))), S(12), r);
-                    r = ffma(fmul(fmul(x, SH_C3[4]), fsub(fsub(fmul(zz, 4.f), xx), yy)), S(13), r);
-                    r = ffma(fmul(fmul(z, SH_C3[5]), fsub(xx, yy)), S(14), r);
-                    r = ffma(fmul(fmul(x, SH_C3[6]), fsub(xx, fmul(yy, 3.f))), S(15), r);
-                }
+                if (deg > 2)
+                    for (int k = 9; k < 16; ++k) r = ffma(l[k], S(k), r);
             }
         }
 #undef S
@@ -252,15 +272,7 @@ static void sh_basis_4d(float x, float y, float z, int deg, float l[16]) {
             l[6] = (float)(((((double)zz + (double)zz) - (double)xx) - (double)yy) * (double)SH_C2[2]); /* :112 */
             l[7] = fmul(xz, SH_C2[3]);
             l[8] = fmul(fsub(xx, yy), SH_C2[4]);
-            if (deg > 2) {
-                l[9] = fmul(fmul(y, SH_C3[0]), fsub(fmul(xx, 3.f), yy));
-                l[10] = fmul(z, fmul(xy, SH_C3[1]));
-                l[11] = fmul(fmul(y, SH_C3[2]), fsub(fsub(fmul(zz, 4.f), xx), yy));
-                l[12] = fmul(fmul(z, SH_C3[3]), fsub(fsub(fadd(zz, zz), fmul(xx, 3.f)), fmul(yy, 3.f)));
-                l[13] = fmul(fmul(x, SH_C3[4]), fsub(fsub(fmul(zz, 4.f), xx), yy));
-                l[14] = fmul(fmul(z, SH_C3[5]), fsub(xx, yy));
-                l[15] = fmul(fmul(x, SH_C3[6]), fsub(xx, fmul(yy, 3.f)));
-            }
+            if (deg > 2) sh_l3(x, y, z, xx, yy, zz, xy, l);
         }
     }
 }
@@ -383,12 +395,12 @@ int oracle_preprocess(const OracleScene* s, OracleGeom* g) {
         cov2d(&Pj, cov3D, &ca, &cb, &cc);
         ca = fadd(ca, 0.3f);
         cc = fadd(cc, 0.3f);
-        const float det = fsub(fmul(ca, cc), fmul(cb, cb));
+        const float det = ffma(ca, cc, -fmul(cb, cb)); /* forward.cu:454, first product fused */
         if (det == 0.0f) continue;
         const float det_inv = 1.f / det;
         const float conx = fmul(cc, det_inv), cony = fmul(det_inv, -cb), conz = fmul(ca, det_inv);
         const float mid = fmul(fadd(ca, cc), 0.5f);
-        const float sq = sqrtf(fmaxf(fsub(fmul(mid, mid), det), 0.1f));
+        const float sq = sqrtf(fmaxf(ffma(mid, mid, -det), 0.1f)); /* :465 */
         const float lam = fmaxf(fadd(mid, sq), fsub(mid, sq));
         const float my_radius = ceilf(fmul(sqrtf(lam), 3.f));
         const float ix = ndc2Pix(projx, s->W), iy = ndc2Pix(projy, s->H);
@@ -514,9 +526,9 @@ void oracle_render_forward(int W, int H, const uint32_t* ranges, const uint32_t*
                 const uint32_t id = point_list[i];
                 const float dx = fsub(means2D[2 * id], pixfx), dy = fsub(means2D[2 * id + 1], pixfy);
                 const float* co = conic_opacity + 4 * id;
-                /* forward.cu:581 as compiled: (fma(dx, dx*A, dy*(dy*C)) * -0.5) - dy*(dx*B) */
-                const float power = fsub(fmul(ffma(dx, fmul(dx, co[0]), fmul(dy, fmul(dy, co[2]))), -0.5f),
-                                         fmul(dy, fmul(dx, co[1])));
+                /* forward.cu:581 as compiled: fma(fma(dx, dx*A, dy*(dy*C)), -0.5, -(dy*(dx*B))) */
+                const float power = ffma(ffma(dx, fmul(dx, co[0]), fmul(dy, fmul(dy, co[2]))), -0.5f,
+                                         -fmul(dy, fmul(dx, co[1])));
                 if (power > 0.0f) continue;
                 const float alpha = fminf(fmul(co[3], expf(power)), 0.99f);
                 if (alpha < 1.0f / 255.0f) continue;
@@ -573,8 +585,8 @@ void oracle_render_backward(int W, int H, const uint32_t* ranges, const uint32_t
                 const uint32_t id = point_list[i];
                 const float dx = fsub(means2D[2 * id], pixfx), dy = fsub(means2D[2 * id + 1], pixfy);
                 const float* co = conic_opacity + 4 * id;
-                const float power = fsub(fmul(ffma(dx, fmul(dx, co[0]), fmul(dy, fmul(dy, co[2]))), -0.5f),
-                                         fmul(dy, fmul(dx, co[1])));
+                const float power = ffma(ffma(dx, fmul(dx, co[0]), fmul(dy, fmul(dy, co[2]))), -0.5f,
+                                         -fmul(dy, fmul(dx, co[1])));
                 if (power > 0.0f) continue;
                 const float G = expf(power);
                 const float alpha = fminf(fmul(co[3], G), 0.99f);

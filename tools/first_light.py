@@ -70,6 +70,9 @@ def relerr(a, b):
     return d / n if n > 0 else d
 
 
+NO_REF = False
+NO_TIMING = False
+
 GRAD_NAMES = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dflows", "dL_dts",
               "dL_dscales", "dL_dscales_t", "dL_drot", "dL_drot_r"]
 
@@ -99,7 +102,7 @@ def run_config(name, cfg, golden_dir=None):
     bg = torch.tensor(cfg.get("bg", (0.0, 0.0, 0.0)), dtype=torch.float32)
     st = synth.raster_settings(cam, sc_cpu, bg=bg, device=dev)
     C = fdgs.ext()
-    ref = oracle_py.ref_module() if oracle_py.ref_available() else None
+    ref = oracle_py.ref_module() if (oracle_py.ref_available() and not NO_REF) else None
     P, W, H = cfg["P"], cfg["W"], cfg["H"]
     a = fwd_args(st, sc)
     mine = C.rasterize_gaussians(*a)
@@ -174,6 +177,8 @@ def run_config(name, cfg, golden_dir=None):
         print("golden written", flush=True)
 
     # timings
+    if NO_TIMING:
+        return
     try:
         t_mf = timeit(lambda: C.rasterize_gaussians(*a))
         t_mb = timeit(lambda: C.rasterize_gaussians_backward(*bwd_args(st, sc, mine, grads)))
@@ -192,7 +197,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="tiny,small,flow,negfov,mid,cfg2,cfg3")
     ap.add_argument("--golden", default=None)
+    ap.add_argument("--no-ref", action="store_true", help="skip the reference (e.g. under ncu)")
+    ap.add_argument("--no-timing", action="store_true")
     args = ap.parse_args()
+    global NO_REF, NO_TIMING
+    NO_REF, NO_TIMING = args.no_ref, args.no_timing
     print(torch.cuda.get_device_name(0), torch.version.cuda, flush=True)
     for name in args.configs.split(","):
         try:
