@@ -5,7 +5,10 @@
 // (reference: rasterizer_impl.cu:199-364, :368-496, :142-154) and the GeometryState /
 // ImageState / BinningState chunk carving (rasterizer_impl.cu:156-195, rasterizer_impl.h:21-73).
 #include <string.h>
+#include <atomic>
+#include <mutex>
 #include <string>
+#include <vector>
 #include "../../include/fdgs.h"
 #include "fdgs_internal.h"
 
@@ -25,9 +28,43 @@ int fail(int code, const std::string& msg) {
             return fail(FDGS_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(_e));            \
     } while (0)
 
-#define FDGS_STAGE(expr, what)                                                                        \
+// ---- measurement hooks (include/fdgs.h: fdgs_profile_*, fdgs_launch_count) -----------------------
+struct ProfEvent {
+    int stage;
+    cudaEvent_t a, b;
+};
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfEvent> g_prof_events;
+std::atomic<long long> g_kernel_launches{0};
+
+struct StageTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    int stage;
+    cudaStream_t stream;
+    StageTimer(int stage_, cudaStream_t s) : stage(stage_), stream(s) {
+        if (g_prof_on) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, stream);
+        }
+    }
+    void stop(int kernels) {
+        g_kernel_launches += kernels;
+        if (a) {
+            cudaEventRecord(b, stream);
+            std::lock_guard<std::mutex> lk(g_prof_mu);
+            g_prof_events.push_back({stage, a, b});
+        }
+    }
+};
+
+// FDGS_STAGE(stage id, kernels launched, launch expression, name)
+#define FDGS_STAGE(sid, nk, expr, what)                                                               \
     do {                                                                                              \
+        StageTimer _t(sid, stream);                                                                   \
         FDGS_CUDA(expr, what);                                                                        \
+        _t.stop(nk);                                                                                  \
         if (debug) {                                                                                  \
             cudaError_t _s = cudaStreamSynchronize(stream);                                           \
             if (_s != cudaSuccess)                                                                    \
@@ -224,8 +261,8 @@ int fdgs_forward(const fdgs_forward_args* a, fdgs_alloc_fn geom_alloc, void* geo
         pp.out_means3D = a->out_means3D; pp.radii = a->radii; pp.means2D = geom.means2D; pp.depths = geom.depths;
         pp.cov3D = geom.cov3D; pp.rgb = geom.rgb; pp.conic_opacity = geom.conic_opacity; pp.clamped = geom.clamped;
         pp.tiles_touched = geom.tiles_touched;
-        FDGS_STAGE(fdgs::launch_preprocess_fwd(pp, stream), "preprocess_fwd");
-        FDGS_STAGE(fdgs::launch_scan(geom.scan_temp, geom.scan_bytes, geom.tiles_touched, geom.point_offsets, P, stream),
+        FDGS_STAGE(0, 1, fdgs::launch_preprocess_fwd(pp, stream), "preprocess_fwd");
+        FDGS_STAGE(1, 2, fdgs::launch_scan(geom.scan_temp, geom.scan_bytes, geom.tiles_touched, geom.point_offsets, P, stream),
                    "scan");
         // the one host synchronisation of the forward (reference: rasterizer_impl.cu:302)
         FDGS_CUDA(cudaMemcpyAsync(&num_rendered, geom.point_offsets + (P - 1), sizeof(int), cudaMemcpyDeviceToHost, stream),
@@ -244,16 +281,16 @@ int fdgs_forward(const fdgs_forward_args* a, fdgs_alloc_fn geom_alloc, void* geo
 
     FDGS_CUDA(cudaMemsetAsync(img.ranges, 0, (size_t)grid_x * grid_y * sizeof(uint2), stream), "ranges memset");
     if (num_rendered > 0) {
-        FDGS_STAGE(fdgs::launch_emit_keys(P, geom.means2D, geom.depths, geom.point_offsets, a->radii, grid_x, grid_y,
+        FDGS_STAGE(2, 1, fdgs::launch_emit_keys(P, geom.means2D, geom.depths, geom.point_offsets, a->radii, grid_x, grid_y,
                                           bin.keys_unsorted, bin.vals_unsorted, stream),
                    "emit_keys");
         int tile_bits = 0;
         while ((1 << tile_bits) < grid_x * grid_y) ++tile_bits;
-        FDGS_STAGE(fdgs::launch_sort_pairs(bin.sort_temp, bin.sort_bytes, bin.keys_unsorted, bin.keys_sorted,
+        FDGS_STAGE(3, 2 + (32 + tile_bits + 7) / 8, fdgs::launch_sort_pairs(bin.sort_temp, bin.sort_bytes, bin.keys_unsorted, bin.keys_sorted,
                                            bin.vals_unsorted, bin.point_list, num_rendered, 32 + tile_bits, stream),
                    "sort");
         const float* colors = a->colors_precomp ? a->colors_precomp : geom.rgb;
-        FDGS_STAGE(fdgs::launch_pack_instances(num_rendered, bin.keys_sorted, bin.point_list, geom.means2D,
+        FDGS_STAGE(4, 1, fdgs::launch_pack_instances(num_rendered, bin.keys_sorted, bin.point_list, geom.means2D,
                                                geom.conic_opacity, colors, geom.depths, a->flows_precomp, bin.recs,
                                                img.ranges, stream),
                    "pack_instances");
@@ -264,7 +301,7 @@ int fdgs_forward(const fdgs_forward_args* a, fdgs_alloc_fn geom_alloc, void* geo
     bp.final_T = img.final_T; bp.n_contrib = img.n_contrib;
     bp.out_color = a->out_color; bp.out_flow = a->out_flow; bp.out_depth = a->out_depth; bp.out_T = a->out_T;
     (void)N;
-    FDGS_STAGE(fdgs::launch_blend_fwd(bp, stream), "blend_fwd");
+    FDGS_STAGE(5, 1, fdgs::launch_blend_fwd(bp, stream), "blend_fwd");
     return FDGS_OK;
 }
 
@@ -296,7 +333,7 @@ int fdgs_backward(const fdgs_backward_args* a, void* stream_v) {
         bp.dL_dpix = a->dL_dpix; bp.dL_depths = a->dL_depths; bp.dL_masks = a->dL_masks; bp.dL_dpix_flow = a->dL_dpix_flow;
         bp.dL_dmean2D = a->dL_dmean2D; bp.dL_dconic = a->dL_dconic; bp.dL_dopacity = a->dL_dopacity;
         bp.dL_dcolor = a->dL_dcolor; bp.dL_dflows = a->dL_dflows;
-        FDGS_STAGE(fdgs::launch_blend_bwd(bp, stream), "blend_bwd");
+        FDGS_STAGE(6, 1, fdgs::launch_blend_bwd(bp, stream), "blend_bwd");
     }
     fdgs::PreprocessBwdParams pb;
     memset(&pb, 0, sizeof(pb));
@@ -320,7 +357,7 @@ int fdgs_backward(const fdgs_backward_args* a, void* stream_v) {
     pb.dL_dscale = a->dL_dscale; pb.dL_dscale_t = a->dL_dscale_t; pb.dL_drot = a->dL_drot; pb.dL_drot_r = a->dL_drot_r;
     if (pb.has_scales && pb.rot_4d && (!a->rotations_r || !a->scales_t || !a->ts || !a->opacities))
         return fail(FDGS_ERR_INVALID_ARG, "rot_4d backward needs rotations_r, scales_t, ts, opacities");
-    FDGS_STAGE(fdgs::launch_preprocess_bwd(pb, stream), "preprocess_bwd");
+    FDGS_STAGE(7, 1, fdgs::launch_preprocess_bwd(pb, stream), "preprocess_bwd");
     return FDGS_OK;
 }
 
@@ -332,6 +369,38 @@ int fdgs_mark_visible(int P, const float* means3D, const float* viewmatrix, cons
               "mark_visible");
     return FDGS_OK;
 }
+
+int fdgs_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = on != 0;
+    return FDGS_OK;
+}
+
+int fdgs_profile_read(double ms[FDGS_NUM_STAGES], long long calls[FDGS_NUM_STAGES]) {
+    std::vector<ProfEvent> ev;
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        ev.swap(g_prof_events);
+    }
+    for (int i = 0; i < FDGS_NUM_STAGES; ++i) {
+        if (ms) ms[i] = 0.0;
+        if (calls) calls[i] = 0;
+    }
+    for (auto& e : ev) {
+        cudaEventSynchronize(e.b);
+        float t = 0.f;
+        cudaEventElapsedTime(&t, e.a, e.b);
+        if (e.stage >= 0 && e.stage < FDGS_NUM_STAGES) {
+            if (ms) ms[e.stage] += t;
+            if (calls) calls[e.stage] += 1;
+        }
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    return FDGS_OK;
+}
+
+long long fdgs_launch_count(void) { return g_kernel_launches.load(); }
 
 int fdgs_debug_export_geom(const char* geom_buffer, int P, float* depths, float* means2D, float* conic_opacity,
                            float* rgb, unsigned char* clamped, unsigned int* tiles_touched, void* stream_v) {

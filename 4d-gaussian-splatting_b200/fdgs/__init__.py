@@ -22,7 +22,11 @@ EXT_PATH = os.path.join(LIB_DIR, "fdgs_C.so")
 ABI_SYMBOLS = (
     "fdgs_version", "fdgs_last_error", "fdgs_geom_bytes", "fdgs_image_bytes", "fdgs_binning_bytes",
     "fdgs_forward", "fdgs_backward", "fdgs_mark_visible", "fdgs_debug_export_geom", "fdgs_debug_export_binning",
+    "fdgs_profile_enable", "fdgs_profile_read", "fdgs_launch_count",
 )
+
+STAGE_NAMES = ("preprocess_fwd", "scan", "emit_keys", "sort", "pack_instances", "blend_fwd", "blend_bwd",
+               "preprocess_bwd")
 
 _lib = None
 _ext = None
@@ -43,6 +47,7 @@ def lib():
         _lib.fdgs_last_error.restype = ctypes.c_char_p
         for n in ("fdgs_geom_bytes", "fdgs_image_bytes", "fdgs_binning_bytes"):
             getattr(_lib, n).restype = ctypes.c_size_t
+        _lib.fdgs_launch_count.restype = ctypes.c_longlong
     return _lib
 
 
@@ -59,6 +64,23 @@ def ext():
         spec.loader.exec_module(mod)
         _ext = mod
     return _ext
+
+
+def profile_enable(on=True):
+    """Per-stage CUDA-event timing inside the library (bench.py)."""
+    lib().fdgs_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """{stage name: (milliseconds, calls)} accumulated since the previous read."""
+    ms = (ctypes.c_double * len(STAGE_NAMES))()
+    calls = (ctypes.c_longlong * len(STAGE_NAMES))()
+    lib().fdgs_profile_read(ms, calls)
+    return {n: (ms[i], calls[i]) for i, n in enumerate(STAGE_NAMES)}
+
+
+def launch_count():
+    return int(lib().fdgs_launch_count())
 
 
 def __getattr__(name):

@@ -209,6 +209,19 @@ int fdgs_debug_export_binning(const char* binning_buffer, const char* image_buff
                               unsigned int* n_contrib /*[H*W]*/,
                               void* stream);
 
+/* Measurement hooks (bench.py): per-stage device time with CUDA events recorded on the launch
+ * stream, and a count of the kernels this library launched.  The reference has no equivalent
+ * (it times whole iterations from Python, train.py:57-58,89,185). */
+#define FDGS_NUM_STAGES 8
+/* stage ids: 0 preprocess_fwd, 1 scan, 2 emit_keys, 3 sort, 4 pack_instances, 5 blend_fwd,
+ *            6 blend_bwd, 7 preprocess_bwd */
+int fdgs_profile_enable(int on);
+/* Synchronises the recorded events, adds up the milliseconds and call counts per stage since the
+ * last read, then resets the accumulators. */
+int fdgs_profile_read(double ms[FDGS_NUM_STAGES], long long calls[FDGS_NUM_STAGES]);
+/* number of CUDA kernels launched by this library since it was loaded */
+long long fdgs_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

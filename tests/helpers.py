@@ -1,0 +1,137 @@
+"""Shared helpers of the parity tests: seeded configurations, runners for the three
+implementations (CUDA path through the extension, CPU oracle, compiled reference) and the
+comparison metrics."""
+import os
+
+import numpy as np
+import torch
+
+from fdgs import synth
+import oracle_py
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+# name -> synthetic configuration.  The ones with a golden_<name>.npz were run through the UNMODIFIED
+# reference kernels on a B200 (tools/first_light.py --golden, see tests/golden/README.md).
+CONFIGS = {
+    "tiny": dict(P=2000, W=128, H=96, seed=11),
+    "small": dict(P=10000, W=256, H=256, seed=1235),
+    "flowbg": dict(P=3000, W=160, H=112, seed=77, flow=True, bg=(0.3, 0.6, 0.1)),
+    "negfov": dict(P=3000, W=160, H=112, seed=78, negative_fov=True, flow=True),
+    "ragged": dict(P=1500, W=101, H=67, seed=5),            # image not a multiple of the 16x16 tile
+    "sh3d": dict(P=3000, W=160, H=112, seed=79, force_sh_3d=True),
+    "dim3": dict(P=3000, W=160, H=112, seed=80, gaussian_dim=3, rot_4d=False),
+    "norot4d": dict(P=3000, W=160, H=112, seed=81, gaussian_dim=4, rot_4d=False),
+    "deg1": dict(P=3000, W=160, H=112, seed=82, sh_degree=1, sh_degree_t=0, M=48),
+    "m16": dict(P=3000, W=160, H=112, seed=83, sh_degree=3, sh_degree_t=0, M=16),
+    "prefilter": dict(P=3000, W=160, H=112, seed=84, prefilter_var=0.01),
+    "mid": dict(P=100000, W=640, H=480, seed=1236),
+    "cfg2": dict(P=500000, W=1352, H=1014, seed=1236),
+    "cfg3": dict(P=2000000, W=1352, H=1014, seed=1237),
+}
+
+GRAD_NAMES = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dflows", "dL_dts",
+              "dL_dscales", "dL_dscales_t", "dL_drot", "dL_drot_r"]
+# same order, names used by oracle_py.backward
+ORACLE_GRAD_KEYS = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dflows", "dL_dts",
+                    "dL_dscales", "dL_dscales_t", "dL_drotations", "dL_drotations_r"]
+
+
+def build(name_or_cfg, device="cpu"):
+    cfg = CONFIGS[name_or_cfg] if isinstance(name_or_cfg, str) else name_or_cfg
+    cam = synth.make_camera(cfg["W"], cfg["H"], negative_fov=cfg.get("negative_fov", False))
+    sc = synth.make_scene(cfg["P"], cam, cfg["seed"], flow=cfg.get("flow", False), M=cfg.get("M", 48),
+                          sh_degree=cfg.get("sh_degree", 3), sh_degree_t=cfg.get("sh_degree_t", 2),
+                          rot_4d=cfg.get("rot_4d", True), gaussian_dim=cfg.get("gaussian_dim", 4),
+                          force_sh_3d=cfg.get("force_sh_3d", False))
+    bg = torch.tensor(cfg.get("bg", (0.0, 0.0, 0.0)), dtype=torch.float32)
+    st = synth.raster_settings(cam, sc, bg=bg, device=device)
+    return cfg, cam, sc.to(device), st
+
+
+def pixel_grads(cfg, device="cpu"):
+    g = torch.Generator().manual_seed(cfg["seed"] + 999)
+    H, W = cfg["H"], cfg["W"]
+    gc = torch.randn(3, H, W, generator=g)
+    gd = 0.1 * torch.randn(1, H, W, generator=g)
+    ga = 0.1 * torch.randn(1, H, W, generator=g)
+    gf = 0.1 * torch.randn(2, H, W, generator=g)
+    return tuple(t.to(device) for t in (gc, gd, ga, gf))
+
+
+def _opt(t, sc, cond=True):
+    return t if cond else torch.Tensor([])
+
+
+def fwd_args(st, sc, cfg):
+    """Positional arguments of _C.rasterize_gaussians (reference: diff_gaussian_rasterization.py:88-119)."""
+    e = torch.Tensor([])
+    four_d = sc.gaussian_dim == 4
+    return (st["bg"], sc.means3D, e, sc.flow_2d, sc.opacities, sc.ts if four_d else e, sc.scales,
+            sc.scales_t if four_d else e, sc.rotations, sc.rotations_r if sc.rot_4d else e, st["scale_modifier"], e,
+            cfg.get("prefilter_var", -1.0), st["viewmatrix"], st["projmatrix"], st["tanfovx"], st["tanfovy"],
+            st["image_height"], st["image_width"], sc.shs, st["sh_degree"], st["sh_degree_t"], st["campos"],
+            st["timestamp"], st["time_duration"], st["rot_4d"], st["gaussian_dim"], st["force_sh_3d"],
+            st["prefiltered"], st["debug"])
+
+
+def bwd_args(st, sc, cfg, fw, grads):
+    e = torch.Tensor([])
+    four_d = sc.gaussian_dim == 4
+    (num_rendered, color, flow, depth, T, radii, geom, binning, img, covs, out_means3D) = fw
+    gc, gd, ga, gf = grads
+    return (st["bg"], sc.means3D, out_means3D, radii, e, sc.flow_2d, sc.opacities, sc.ts if four_d else e, sc.scales,
+            sc.scales_t if four_d else e, sc.rotations, sc.rotations_r if sc.rot_4d else e, st["scale_modifier"], e,
+            cfg.get("prefilter_var", -1.0), st["viewmatrix"], st["projmatrix"], st["tanfovx"], st["tanfovy"], gc, gd, ga,
+            gf, sc.shs, st["sh_degree"], st["sh_degree_t"], st["campos"], st["timestamp"], st["time_duration"],
+            st["rot_4d"], st["gaussian_dim"], st["force_sh_3d"], geom, num_rendered, binning, img, st["debug"])
+
+
+def oracle_inputs(st, sc, cfg):
+    four_d = sc.gaussian_dim == 4
+    return oracle_py.OracleInputs(st, sc.means3D, sc.opacities, shs=sc.shs, flow_2d=sc.flow_2d,
+                                  ts=sc.ts if four_d else None, scales=sc.scales,
+                                  scales_t=sc.scales_t if four_d else None, rotations=sc.rotations,
+                                  rotations_r=sc.rotations_r if sc.rot_4d else None,
+                                  prefilter_var=cfg.get("prefilter_var", -1.0))
+
+
+def bitdiff(a, b):
+    """number of elements whose bit patterns differ"""
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if a.dtype.kind == "f":
+        return int((a.view(np.int32) != b.view(np.int32)).sum())
+    return int((a.astype(np.int64) != b.astype(np.int64)).sum())
+
+
+def max_rel(a, b):
+    """max-norm relative error ||a-b||_inf / ||b||_inf  """
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    n = np.abs(b).max() if b.size else 0.0
+    d = np.abs(a - b).max() if b.size else 0.0
+    return d / n if n > 0 else d
+
+
+def l2_rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    n = np.sqrt((b * b).sum())
+    return np.sqrt(((a - b) ** 2).sum()) / n if n > 0 else np.sqrt(((a - b) ** 2).sum())
+
+
+def psnr(a, b):
+    mse = float(((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2).mean())
+    return 200.0 if mse == 0 else 10.0 * np.log10(1.0 / mse)
+
+
+def golden(name):
+    path = os.path.join(GOLDEN_DIR, "golden_%s.npz" % name)
+    return np.load(path) if os.path.exists(path) else None
+
+
+def to_np(t):
+    return t.detach().cpu().numpy()

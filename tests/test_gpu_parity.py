@@ -1,0 +1,373 @@
+"""GPU (-m gpu): the parity tests proper.  Everything goes through the reference-facing boundary
+(the `_C`-compatible extension over the C-ABI, and the GaussianRasterizer / render() API on top).
+
+Three checkers, strongest first:
+  1. golden vectors produced by the UNMODIFIED reference kernels (tests/golden/*.npz)  -> bit-exact
+     forward (every tensor), gradients within the reference's own atomic-order noise;
+  2. the compiled reference itself (oracle/_ref, when the .so travelled to the box), at the
+     BASELINE sizes (500k / 2M Gaussians, 1352x1014)                                   -> same bar;
+  3. the CPU oracle on seeded inputs the oracle finishes in seconds, including the branches the
+     golden set does not cover (3D Gaussians, 3D SH, no-rot 4D, low SH degree, M=16, prefilter,
+     ragged image sizes, precomputed colours / covariances).
+Plus size-independent properties at full size: sortedness of the instance list, range
+consistency, run-to-run determinism of the forward, linearity and locality of the backward.
+"""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+import oracle_py
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def C():
+    import fdgs
+    return fdgs.ext()   # raises if the CUDA extension is missing -- there is no fallback path
+
+
+def run_cuda(C, name_or_cfg, with_backward=True, grads=None):
+    cfg, cam, sc, st = helpers.build(name_or_cfg, device=DEV)
+    fw = C.rasterize_gaussians(*helpers.fwd_args(st, sc, cfg))
+    out = dict(cfg=cfg, sc=sc, st=st, fw=fw)
+    P, W, H = cfg["P"], cfg["W"], cfg["H"]
+    geom = C.debug_export_geom(fw[6], P)
+    binning = C.debug_export_binning(fw[7], fw[8], fw[0], W, H)
+    out.update(depths=geom[0], means2D=geom[1], conic_opacity=geom[2], rgb=geom[3], clamped=geom[4], tiles=geom[5],
+               point_list=binning[0], ranges=binning[1], n_contrib=binning[2])
+    if with_backward:
+        grads = grads if grads is not None else helpers.pixel_grads(cfg, device=DEV)
+        out["grads_in"] = grads
+        out["bw"] = C.rasterize_gaussians_backward(*helpers.bwd_args(st, sc, cfg, fw, grads))
+    torch.cuda.synchronize()
+    return out
+
+
+def clamp_bits_to_bools(c):
+    return torch.stack([(c >> i) & 1 for i in range(3)], 1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# 1. golden vectors from the reference kernels
+# ---------------------------------------------------------------------------------------------------
+GOLDEN_CASES = ["tiny", "small", "flowbg", "negfov", "ragged", "sh3d", "dim3", "norot4d", "deg1", "m16", "prefilter"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_forward_bit_exact_vs_golden(C, name):
+    G = helpers.golden(name)
+    if G is None:
+        pytest.skip("no golden fixture for %s" % name)
+    o = run_cuda(C, name, with_backward=False)
+    fw = o["fw"]
+    np_ = helpers.to_np
+    assert fw[0] == int(G["num_rendered"])
+    assert helpers.bitdiff(np_(fw[5]), G["radii"]) == 0
+    assert helpers.bitdiff(np_(o["point_list"]), G["point_list"]) == 0
+    assert helpers.bitdiff(np_(o["ranges"]), G["ranges"]) == 0
+    assert helpers.bitdiff(np_(o["n_contrib"]).reshape(-1), G["n_contrib"]) == 0
+    vis = G["radii"] > 0
+    assert helpers.bitdiff(np_(o["tiles"]), G["tiles_touched"]) == 0
+    assert helpers.bitdiff(np_(fw[10]), G["out_means3D"]) == 0
+    for ours, ref in ((o["depths"], "depths"), (o["means2D"], "means2D"), (o["conic_opacity"], "conic_opacity"),
+                      (o["rgb"], "rgb"), (fw[9], "covs3D")):
+        assert helpers.bitdiff(np_(ours)[vis], G[ref][vis]) == 0, ref
+    assert helpers.bitdiff(np_(clamp_bits_to_bools(o["clamped"]))[vis], G["clamped"][vis]) == 0
+    for idx, key in ((1, "color"), (2, "flow"), (3, "depth"), (4, "T")):
+        assert helpers.bitdiff(np_(fw[idx]), G[key]) == 0, key
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_backward_vs_golden(C, name):
+    G = helpers.golden(name)
+    if G is None:
+        pytest.skip("no golden fixture for %s" % name)
+    o = run_cuda(C, name)
+    for gname, ours in zip(helpers.GRAD_NAMES, o["bw"]):
+        ref = G["grad_" + gname]
+        if ref.size == 0:
+            continue
+        a = helpers.to_np(ours).reshape(ref.shape)
+        # the reference accumulates with unordered fp32 atomics: norm-wise 1e-4, max-norm looser
+        assert helpers.l2_rel(a, ref) < 1e-4, gname
+        assert helpers.max_rel(a, ref) < 2e-3, gname
+
+
+# ---------------------------------------------------------------------------------------------------
+# 2. the compiled reference at BASELINE sizes
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["mid", "cfg2", "cfg3"])
+def test_full_size_vs_compiled_reference(C, name):
+    if not oracle_py.ref_available():
+        pytest.skip("oracle/_ref/ref_rasterizer.so not present")
+    ref = oracle_py.ref_module()
+    o = run_cuda(C, name)
+    cfg, sc, st, fw = o["cfg"], o["sc"], o["st"], o["fw"]
+    P, W, H = cfg["P"], cfg["W"], cfg["H"]
+    rf = ref.rasterize_gaussians(*helpers.fwd_args(st, sc, cfg))
+    rb = ref.rasterize_gaussians_backward(*helpers.bwd_args(st, sc, cfg, rf, o["grads_in"]))
+    rb2 = ref.rasterize_gaussians_backward(*helpers.bwd_args(st, sc, cfg, rf, o["grads_in"]))
+    torch.cuda.synchronize()
+    eq = lambda a, b: bool(torch.equal(a.contiguous().view(torch.int32), b.contiguous().view(torch.int32)))
+    assert fw[0] == rf[0]
+    assert eq(fw[5], rf[5])                                                  # radii
+    assert eq(o["point_list"], oracle_py.ref_binning_point_list(rf[7], rf[0]))   # tile assignment + order
+    ri = oracle_py.ref_image_views(rf[8], W * H)
+    assert eq(o["n_contrib"].view(-1), ri["n_contrib"])
+    for i in (1, 2, 3, 4, 10):                                               # color, flow, depth, T, out_means3D
+        assert eq(fw[i], rf[i]), i
+    vis = rf[5] > 0
+    assert eq(fw[9][vis], rf[9][vis])                                        # cov3D
+    # gradients: no worse than a few times the reference's own run-to-run noise (atomics), and
+    # 1e-4 in the L2 sense for the quantities accumulated by the blend kernel
+    for gname, a, b, b2 in zip(helpers.GRAD_NAMES, o["bw"], rb, rb2):
+        if b.numel() == 0:
+            continue
+        scale = b.abs().max().item()
+        err = (a - b).abs().max().item() / scale
+        noise = (b2 - b).abs().max().item() / scale
+        l2 = ((a - b).double().norm() / b.double().norm()).item()
+        assert l2 < 1e-4 or l2 < 5 * ((b2 - b).double().norm() / b.double().norm()).item(), (gname, l2)
+        assert err < max(1e-4, 8 * noise), (gname, err, noise)
+
+
+# ---------------------------------------------------------------------------------------------------
+# 3. the CPU oracle, including branches without golden coverage
+# ---------------------------------------------------------------------------------------------------
+ORACLE_CASES = ["tiny", "flowbg", "negfov", "ragged", "sh3d", "dim3", "norot4d", "deg1", "m16", "prefilter"]
+
+
+@pytest.mark.parametrize("name", ORACLE_CASES)
+def test_vs_cpu_oracle(C, name):
+    o = run_cuda(C, name)
+    cfg, fw = o["cfg"], o["fw"]
+    cfg_c, cam, sc_c, st_c = helpers.build(name)
+    inp = helpers.oracle_inputs(st_c, sc_c, cfg_c)
+    f = oracle_py.forward(inp)
+    np_ = helpers.to_np
+    assert fw[0] == f["num_rendered"]
+    assert helpers.bitdiff(np_(fw[5]), f["radii"]) == 0
+    assert helpers.bitdiff(np_(o["point_list"]), f["point_list"]) == 0
+    assert helpers.bitdiff(np_(o["ranges"]), f["ranges"]) == 0
+    vis = f["radii"] > 0
+    assert helpers.bitdiff(np_(fw[10]), f["out_means3D"]) == 0
+    for ours, key in ((o["depths"], "depths"), (o["means2D"], "means2D"), (o["rgb"], "rgb"), (fw[9], "cov3D")):
+        assert helpers.bitdiff(np_(ours)[vis], f[key][vis]) == 0, key
+    assert helpers.bitdiff(np_(o["conic_opacity"])[vis][:, :3], f["conic_opacity"][vis][:, :3]) == 0
+    assert helpers.max_rel(np_(o["conic_opacity"])[vis][:, 3], f["conic_opacity"][vis][:, 3]) < 1e-6   # MUFU vs libm
+    assert helpers.bitdiff(np_(o["n_contrib"]), f["n_contrib"]) <= 2
+    for idx, key in ((1, "color"), (2, "flow"), (3, "depth")):
+        assert helpers.max_rel(np_(fw[idx]), f[key]) < 1e-5, key
+    assert helpers.psnr(np_(fw[1]), f["color"]) > 100
+    g = oracle_py.backward(inp, f, *[np_(t) for t in o["grads_in"]])
+    for gname, okey, ours in zip(helpers.GRAD_NAMES, helpers.ORACLE_GRAD_KEYS, o["bw"]):
+        ref = g[okey]
+        if ref.size == 0:
+            continue
+        a = np_(ours).reshape(ref.shape)
+        assert helpers.l2_rel(a, ref) < 1e-4, gname
+        assert helpers.max_rel(a, ref) < 1e-3, gname
+
+
+def test_precomputed_colors_and_covariance_vs_oracle(C):
+    """colors_precomp / cov3D_precomp branches (reference: forward.cu:411-414,476; backward.cu:897,908)."""
+    cfg, cam, sc, st = helpers.build("tiny", device=DEV)
+    cfg_c, _, sc_c, st_c = helpers.build("tiny")
+    g = torch.Generator().manual_seed(3)
+    colors = torch.rand(cfg["P"], 3, generator=g)
+    A = 0.05 * torch.randn(cfg["P"], 3, 3, generator=g)
+    cov = A @ A.transpose(1, 2) + 1e-4 * torch.eye(3)
+    cov6 = torch.stack([cov[:, 0, 0], cov[:, 0, 1], cov[:, 0, 2], cov[:, 1, 1], cov[:, 1, 2], cov[:, 2, 2]], 1).contiguous()
+    e = torch.Tensor([])
+    args = (st["bg"], sc.means3D, colors.to(DEV), sc.flow_2d, sc.opacities, e, e, e, e, e, 1.0, cov6.to(DEV), -1.0,
+            st["viewmatrix"], st["projmatrix"], st["tanfovx"], st["tanfovy"], cfg["H"], cfg["W"], e, 0, 0, st["campos"],
+            st["timestamp"], st["time_duration"], False, 3, False, False, False)
+    fw = C.rasterize_gaussians(*args)
+    st3 = dict(st_c)
+    st3.update(rot_4d=False, gaussian_dim=3, sh_degree=0, sh_degree_t=0)
+    inp = oracle_py.OracleInputs(st3, sc_c.means3D, sc_c.opacities, colors_precomp=colors, flow_2d=sc_c.flow_2d,
+                                 cov3D_precomp=cov6)
+    f = oracle_py.forward(inp)
+    np_ = helpers.to_np
+    assert fw[0] == f["num_rendered"]
+    assert helpers.bitdiff(np_(fw[5]), f["radii"]) == 0
+    assert helpers.max_rel(np_(fw[1]), f["color"]) < 1e-5
+    grads = helpers.pixel_grads(cfg, device=DEV)
+    (num_rendered, color, flow, depth, T, radii, geom, binning, img, covs, out_means3D) = fw
+    bw = C.rasterize_gaussians_backward(st["bg"], sc.means3D, out_means3D, radii, colors.to(DEV), sc.flow_2d, sc.opacities,
+                                        e, e, e, e, e, 1.0, cov6.to(DEV), -1.0, st["viewmatrix"], st["projmatrix"],
+                                        st["tanfovx"], st["tanfovy"], *grads, e, 0, 0, st["campos"], st["timestamp"],
+                                        st["time_duration"], False, 3, False, geom, num_rendered, binning, img, False)
+    go = oracle_py.backward(inp, f, *[np_(t) for t in grads])
+    for gname, okey, ours in zip(helpers.GRAD_NAMES, helpers.ORACLE_GRAD_KEYS, bw):
+        ref = go[okey]
+        if ref.size == 0 or gname in ("dL_dsh",):
+            continue
+        assert helpers.l2_rel(np_(ours).reshape(ref.shape), ref) < 1e-4, gname
+
+
+def test_empty_and_degenerate_inputs(C):
+    cfg, cam, sc, st = helpers.build("tiny", device=DEV)
+    # P = 0 (reference: rasterize_points.cu:97,215)
+    sc0 = helpers.synth.make_scene(0, cam, 1).to(DEV)
+    fw = C.rasterize_gaussians(*helpers.fwd_args(st, sc0, cfg))
+    assert fw[0] == 0 and fw[5].numel() == 0
+    assert torch.all(fw[4] == 1.0) and torch.all(fw[1] == 0.0)
+    # everything behind the camera / outside the time window: nothing rendered, background only
+    sc1 = helpers.build("tiny", device=DEV)[2]
+    sc1.means3D[:, 2] = -5.0
+    st_bg = dict(st)
+    st_bg["bg"] = torch.tensor([0.1, 0.2, 0.3], device=DEV)
+    fw = C.rasterize_gaussians(*helpers.fwd_args(st_bg, sc1, cfg))
+    assert fw[0] == 0 and int((fw[5] > 0).sum()) == 0
+    assert torch.allclose(fw[1][:, 5, 7], torch.tensor([0.1, 0.2, 0.3], device=DEV))
+    grads = helpers.pixel_grads(cfg, device=DEV)
+    bw = C.rasterize_gaussians_backward(*helpers.bwd_args(st_bg, sc1, cfg, fw, grads))
+    assert all(float(t.abs().sum()) == 0.0 for t in bw)
+    # mark_visible (reference: rasterizer_impl.cu:54-67)
+    vis = C.mark_visible(sc.means3D, st["viewmatrix"], st["projmatrix"])
+    assert torch.equal(vis, sc.means3D[:, 2] > 0.2)
+
+
+# ---------------------------------------------------------------------------------------------------
+# size-independent properties at the BASELINE size
+# ---------------------------------------------------------------------------------------------------
+def test_full_size_properties(C):
+    o = run_cuda(C, "cfg3")
+    cfg, fw = o["cfg"], o["fw"]
+    R = fw[0]
+    P, W, H = cfg["P"], cfg["W"], cfg["H"]
+    assert R == int(o["tiles"].long().sum())
+    ranges = o["ranges"].long()
+    pl = o["point_list"].long()
+    # ranges tile the instance list exactly
+    nonempty = ranges[:, 1] > ranges[:, 0]
+    starts = ranges[nonempty, 0]
+    ends = ranges[nonempty, 1]
+    assert int(starts[0]) == 0 and int(ends[-1]) == R and torch.equal(starts[1:], ends[:-1])
+    # within every tile the list is sorted by (depth bits, Gaussian index): a checksum-free sortedness test
+    depth_bits = o["depths"].view(torch.int32).long()[pl]
+    tile_of = torch.repeat_interleave(torch.arange(ranges.shape[0], device=DEV), (ranges[:, 1] - ranges[:, 0]))
+    key = (tile_of << 32) | depth_bits
+    assert bool(torch.all(key[1:] >= key[:-1]))
+    same = key[1:] == key[:-1]
+    assert bool(torch.all(pl[1:][same] > pl[:-1][same]))
+    # n_contrib never exceeds the tile's list length
+    gx = (W + 15) // 16
+    ys, xs = torch.meshgrid(torch.arange(H, device=DEV), torch.arange(W, device=DEV), indexing="ij")
+    tl = (ys // 16) * gx + xs // 16
+    assert bool(torch.all(o["n_contrib"].long() <= (ranges[:, 1] - ranges[:, 0])[tl]))
+    # forward is deterministic: bit-identical on a second run
+    o2 = run_cuda(C, "cfg3", with_backward=False)
+    for i in (1, 2, 3, 4, 5, 10):
+        assert torch.equal(fw[i], o2["fw"][i])
+    # backward: linear in the upstream gradients, zero in -> zero out, nothing for unrendered Gaussians
+    g1 = o["grads_in"]
+    g2 = tuple(torch.randn_like(t) for t in g1)
+    st, sc = o["st"], o["sc"]
+    b2 = C.rasterize_gaussians_backward(*helpers.bwd_args(st, sc, cfg, fw, g2))
+    b12 = C.rasterize_gaussians_backward(*helpers.bwd_args(st, sc, cfg, fw, tuple(2.0 * a - 0.5 * b for a, b in zip(g1, g2))))
+    bz = C.rasterize_gaussians_backward(*helpers.bwd_args(st, sc, cfg, fw, tuple(torch.zeros_like(t) for t in g1)))
+    invisible = fw[5] <= 0
+    for name, a, b, ab, z in zip(helpers.GRAD_NAMES, o["bw"], b2, b12, bz):
+        lin = 2.0 * a - 0.5 * b
+        # linear up to fp32 round-off; the ill-conditioned covariance chain amplifies it (the reference's
+        # own run-to-run noise on these tensors is ~1e-3 at this size)
+        assert ((ab - lin).double().norm() / lin.double().norm()).item() < 3e-3, name
+        assert float(z.abs().sum()) == 0.0, name
+        assert float(a[invisible].abs().sum()) == 0.0, name
+
+
+# ---------------------------------------------------------------------------------------------------
+# the Python API on top (GaussianRasterizer + render()), autograd end to end
+# ---------------------------------------------------------------------------------------------------
+class _Model:
+    """Duck-typed stand-in for the reference's GaussianModel getters (scene/gaussian_model.py:179-251)."""
+
+    def __init__(self, sc):
+        self.sc = sc
+        self.get_xyz = sc.means3D.clone().requires_grad_(True)
+        self.get_opacity = sc.opacities.clone().requires_grad_(True)
+        self.get_scaling = sc.scales.clone().requires_grad_(True)
+        self.get_scaling_t = sc.scales_t.clone().requires_grad_(True)
+        self.get_rotation = sc.rotations.clone().requires_grad_(True)
+        self.get_rotation_r = sc.rotations_r.clone().requires_grad_(True)
+        self.get_t = sc.ts.clone().requires_grad_(True)
+        self.get_features = sc.shs.clone().requires_grad_(True)
+        self.active_sh_degree, self.active_sh_degree_t = sc.sh_degree, sc.sh_degree_t
+        self.time_duration = [0.0, sc.time_duration]
+        self.rot_4d, self.gaussian_dim, self.force_sh_3d = sc.rot_4d, sc.gaussian_dim, sc.force_sh_3d
+        self.prefilter_var = -1.0
+        self.get_max_sh_channels = sc.shs.shape[1]
+
+
+class _Pipe:
+    convert_SHs_python = False
+    compute_cov3D_python = False
+    debug = False
+    env_map_res = 0
+
+
+def test_render_api_end_to_end(C):
+    from gaussian_renderer import render
+    cfg, cam, sc, st = helpers.build("small", device=DEV)
+    pc = _Model(sc)
+    bg = torch.zeros(3, device=DEV)
+    pkg = render(cam.to(DEV), pc, _Pipe(), bg)
+    assert set(pkg) == {"render", "viewspace_points", "visibility_filter", "radii", "depth", "alpha", "flow"}
+    G = helpers.golden("small")
+    assert helpers.bitdiff(helpers.to_np(pkg["render"]), G["color"]) == 0
+    assert helpers.bitdiff(helpers.to_np(pkg["radii"]), G["radii"]) == 0
+    assert helpers.max_rel(helpers.to_np(pkg["alpha"]), 1.0 - G["T"]) < 1e-6
+    gc, gd, ga, gf = helpers.pixel_grads(cfg, device=DEV)
+    loss = (pkg["render"] * gc).sum() + (pkg["depth"] * gd).sum() + (pkg["alpha"] * ga).sum() + (pkg["flow"] * gf).sum()
+    loss.backward()
+    checks = (("dL_dmeans3D", pc.get_xyz), ("dL_dopacity", pc.get_opacity), ("dL_dscales", pc.get_scaling),
+              ("dL_dscales_t", pc.get_scaling_t), ("dL_drot", pc.get_rotation), ("dL_drot_r", pc.get_rotation_r),
+              ("dL_dts", pc.get_t), ("dL_dsh", pc.get_features), ("dL_dmeans2D", pkg["viewspace_points"]))
+    for gname, t in checks:
+        ref = G["grad_" + gname]
+        assert t.grad is not None, gname
+        assert helpers.l2_rel(helpers.to_np(t.grad).reshape(ref.shape), ref) < 1e-4, gname
+    # a loss on the image only (the reference's training loss, train.py:115-117): the unused outputs
+    # contribute nothing -- same gradients as passing explicit zero upstream gradients
+    pc2 = _Model(sc)
+    pkg2 = render(cam.to(DEV), pc2, _Pipe(), bg)
+    (pkg2["render"] * gc).sum().backward()
+    fw = C.rasterize_gaussians(*helpers.fwd_args(st, sc, cfg))
+    z = lambda t: torch.zeros_like(t)
+    bw = C.rasterize_gaussians_backward(*helpers.bwd_args(st, sc, cfg, fw, (gc, z(gd), z(ga), z(gf))))
+    assert helpers.l2_rel(helpers.to_np(pc2.get_xyz.grad), helpers.to_np(bw[3])) < 1e-5
+    assert helpers.l2_rel(helpers.to_np(pc2.get_features.grad), helpers.to_np(bw[5])) < 1e-5
+
+
+def test_render_python_preprocess_flags(C):
+    """compute_cov3D_python / convert_SHs_python branches of render() (reference: __init__.py:73-81,98-111)
+    against the all-CUDA path: same image up to the documented SH-direction quirk."""
+    from gaussian_renderer import render, pyprep
+    cfg, cam, sc, st = helpers.build("tiny", device=DEV)
+
+    class M(_Model):
+        def get_current_covariance_and_mean_offset(self, mod, timestamp):
+            return pyprep.conditional_covariance_and_offset(torch.cat([self.get_scaling, self.get_scaling_t], 1), mod,
+                                                            self.get_rotation, self.get_rotation_r, timestamp - self.get_t)
+
+        def get_marginal_t(self, timestamp):
+            return pyprep.marginal_t(torch.cat([self.get_scaling, self.get_scaling_t], 1), 1.0, self.get_rotation,
+                                     self.get_rotation_r, self.get_t, timestamp)
+
+    class P2(_Pipe):
+        compute_cov3D_python = True
+        convert_SHs_python = True
+
+    bg = torch.zeros(3, device=DEV)
+    a = render(cam.to(DEV), M(sc), _Pipe(), bg)
+    b = render(cam.to(DEV), M(sc), P2(), bg)
+    assert a["radii"].shape == b["radii"].shape
+    agree = (a["radii"] > 0) == (b["radii"] > 0)
+    assert float(agree.float().mean()) > 0.995
+    assert helpers.psnr(helpers.to_np(a["render"]), helpers.to_np(b["render"])) > 35.0

@@ -18,40 +18,15 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "4d-gaussian-splatting_b200"))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import fdgs  # noqa: E402
 from fdgs import synth  # noqa: E402
 import oracle_py  # noqa: E402
 
-CONFIGS = {
-    "tiny": dict(P=2000, W=128, H=96, seed=11),
-    "small": dict(P=10000, W=256, H=256, seed=1235),
-    "flow": dict(P=20000, W=320, H=240, seed=77, flow=True, bg=(0.3, 0.6, 0.1)),
-    "negfov": dict(P=20000, W=320, H=240, seed=78, negative_fov=True, flow=True),
-    "mid": dict(P=100000, W=640, H=480, seed=1236),
-    "cfg2": dict(P=500000, W=1352, H=1014, seed=1236),
-    "cfg3": dict(P=2000000, W=1352, H=1014, seed=1237),
-}
+import helpers  # noqa: E402  (tests/helpers.py: the shared configuration table and argument builders)
 
-
-def fwd_args(st, sc, prefilter_var=-1.0):
-    e = torch.Tensor([])
-    return (st["bg"], sc.means3D, e, sc.flow_2d, sc.opacities, sc.ts, sc.scales, sc.scales_t, sc.rotations,
-            sc.rotations_r, st["scale_modifier"], e, prefilter_var, st["viewmatrix"], st["projmatrix"], st["tanfovx"],
-            st["tanfovy"], st["image_height"], st["image_width"], sc.shs, st["sh_degree"], st["sh_degree_t"],
-            st["campos"], st["timestamp"], st["time_duration"], st["rot_4d"], st["gaussian_dim"], st["force_sh_3d"],
-            st["prefiltered"], st["debug"])
-
-
-def bwd_args(st, sc, fw, grads, prefilter_var=-1.0):
-    e = torch.Tensor([])
-    (num_rendered, color, flow, depth, T, radii, geom, binning, img, covs, out_means3D) = fw
-    gc, gd, ga, gf = grads
-    return (st["bg"], sc.means3D, out_means3D, radii, e, sc.flow_2d, sc.opacities, sc.ts, sc.scales, sc.scales_t,
-            sc.rotations, sc.rotations_r, st["scale_modifier"], e, prefilter_var, st["viewmatrix"], st["projmatrix"],
-            st["tanfovx"], st["tanfovy"], gc, gd, ga, gf, sc.shs, st["sh_degree"], st["sh_degree_t"], st["campos"],
-            st["timestamp"], st["time_duration"], st["rot_4d"], st["gaussian_dim"], st["force_sh_3d"], geom,
-            num_rendered, binning, img, st["debug"])
+CONFIGS = helpers.CONFIGS
 
 
 def bitdiff(a, b):
@@ -96,25 +71,16 @@ def run_config(name, cfg, golden_dir=None):
     print("=" * 100)
     print("CONFIG", name, cfg, flush=True)
     dev = torch.device("cuda:0")
-    cam = synth.make_camera(cfg["W"], cfg["H"], negative_fov=cfg.get("negative_fov", False))
-    sc_cpu = synth.make_scene(cfg["P"], cam, cfg["seed"], flow=cfg.get("flow", False))
-    sc = sc_cpu.to(dev)
-    bg = torch.tensor(cfg.get("bg", (0.0, 0.0, 0.0)), dtype=torch.float32)
-    st = synth.raster_settings(cam, sc_cpu, bg=bg, device=dev)
+    cfg, cam, sc, st = helpers.build(cfg, device=dev)
     C = fdgs.ext()
     ref = oracle_py.ref_module() if (oracle_py.ref_available() and not NO_REF) else None
     P, W, H = cfg["P"], cfg["W"], cfg["H"]
-    a = fwd_args(st, sc)
+    a = helpers.fwd_args(st, sc, cfg)
     mine = C.rasterize_gaussians(*a)
     torch.cuda.synchronize()
     print("mine: num_rendered", mine[0], "visible", int((mine[5] > 0).sum()), flush=True)
-    g = torch.Generator().manual_seed(cfg["seed"] + 999)
-    gc = torch.randn(3, H, W, generator=g).to(dev)
-    gd = (0.1 * torch.randn(1, H, W, generator=g)).to(dev)
-    ga = (0.1 * torch.randn(1, H, W, generator=g)).to(dev)
-    gf = (0.1 * torch.randn(2, H, W, generator=g)).to(dev)
-    grads = (gc, gd, ga, gf)
-    mine_b = C.rasterize_gaussians_backward(*bwd_args(st, sc, mine, grads))
+    grads = helpers.pixel_grads(cfg, device=dev)
+    mine_b = C.rasterize_gaussians_backward(*helpers.bwd_args(st, sc, cfg, mine, grads))
     torch.cuda.synchronize()
     mg = C.debug_export_geom(mine[6], P)
     mb = C.debug_export_binning(mine[7], mine[8], mine[0], W, H)
@@ -124,7 +90,7 @@ def run_config(name, cfg, golden_dir=None):
     if ref is not None:
         rf = ref.rasterize_gaussians(*a)
         torch.cuda.synchronize()
-        rb = ref.rasterize_gaussians_backward(*bwd_args(st, sc, rf, grads))
+        rb = ref.rasterize_gaussians_backward(*helpers.bwd_args(st, sc, cfg, rf, grads))
         torch.cuda.synchronize()
         print("ref : num_rendered", rf[0], "visible", int((rf[5] > 0).sum()))
         vis = rf[5] > 0
@@ -149,7 +115,7 @@ def run_config(name, cfg, golden_dir=None):
         print("-- images: #bitwise-different / maxrel")
         for nm, i in (("color", 1), ("flow", 2), ("depth", 3), ("T", 4)):
             print("%-16s diff=%d  maxrel=%.3e" % (nm, bitdiff(mine[i], rf[i]), relerr(mine[i], rf[i])))
-        rb2 = ref.rasterize_gaussians_backward(*bwd_args(st, sc, rf, grads))
+        rb2 = ref.rasterize_gaussians_backward(*helpers.bwd_args(st, sc, cfg, rf, grads))
         print("-- gradients: maxrel(mine vs ref)   [reference self-noise run-to-run]")
         for nm, m_, r_, r2 in zip(GRAD_NAMES, mine_b, rb, rb2):
             if r_.numel() == 0:
@@ -158,7 +124,7 @@ def run_config(name, cfg, golden_dir=None):
     else:
         print("(reference module not available)")
 
-    if golden_dir and ref is not None and P <= 20000:
+    if golden_dir and ref is not None and P <= 10000:
         os.makedirs(golden_dir, exist_ok=True)
         rpl = oracle_py.ref_binning_point_list(rf[7], rf[0]) if rf[0] > 0 else torch.zeros(0, dtype=torch.int32)
         ri = oracle_py.ref_image_views(rf[8], W * H)
@@ -181,11 +147,11 @@ def run_config(name, cfg, golden_dir=None):
         return
     try:
         t_mf = timeit(lambda: C.rasterize_gaussians(*a))
-        t_mb = timeit(lambda: C.rasterize_gaussians_backward(*bwd_args(st, sc, mine, grads)))
+        t_mb = timeit(lambda: C.rasterize_gaussians_backward(*helpers.bwd_args(st, sc, cfg, mine, grads)))
         line = "TIMING %s mine fwd %.3f ms bwd %.3f ms" % (name, t_mf, t_mb)
         if ref is not None:
             t_rf = timeit(lambda: ref.rasterize_gaussians(*a))
-            t_rb = timeit(lambda: ref.rasterize_gaussians_backward(*bwd_args(st, sc, rf, grads)))
+            t_rb = timeit(lambda: ref.rasterize_gaussians_backward(*helpers.bwd_args(st, sc, cfg, rf, grads)))
             line += " | ref fwd %.3f ms bwd %.3f ms | speedup fwd %.2fx bwd %.2fx total %.2fx" % (
                 t_rf, t_rb, t_rf / t_mf, t_rb / t_mb, (t_rf + t_rb) / (t_mf + t_mb))
         print(line, flush=True)
@@ -195,7 +161,7 @@ def run_config(name, cfg, golden_dir=None):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="tiny,small,flow,negfov,mid,cfg2,cfg3")
+    ap.add_argument("--configs", default="tiny,small,flowbg,negfov,ragged,sh3d,dim3,norot4d,deg1,m16,prefilter,mid,cfg2,cfg3")
     ap.add_argument("--golden", default=None)
     ap.add_argument("--no-ref", action="store_true", help="skip the reference (e.g. under ncu)")
     ap.add_argument("--no-timing", action="store_true")
