@@ -1,152 +1,358 @@
-// binning.cu -- tile binning: offsets scan, key emission, radix sort, instance packing.
+// binning.cu -- tile binning: per-tile counting, offsets, scatter, per-tile sort + instance packing.
 //
-// Replaces, in the reference: cub::DeviceScan::InclusiveSum (rasterizer_impl.cu:298),
-// duplicateWithKeys (:71-112), cub::DeviceRadixSort::SortPairs (:325-330), the ranges memset +
-// identifyTileRanges (:117-139, :332-339).
+// Replaces, in the reference: cub::DeviceScan::InclusiveSum over P Gaussians
+// (rasterizer_impl.cu:298), duplicateWithKeys (:71-112), the 64-bit cub::DeviceRadixSort::SortPairs
+// over all R instances (:325-330), the ranges memset + identifyTileRanges (:117-139, :332-339).
 //
-// The sorted order is the contract ("tile assignment bit-exact"): instances are ordered by
-// (tile id, depth bits) with ties broken by emission order = Gaussian index order, exactly what
-// the reference's stable LSD sort of (tile<<32 | depth_bits) produces.  We sort the same keys but
-// only over the live bits [0, 32 + ceil(log2(#tiles))) -- the upper key bits are zero, so the
-// result is identical to the reference's 64-bit sort (which hard-codes bit = 32,
-// rasterizer_impl.cu:322).
+// The contract is the ORDER of every tile's work list ("tile assignment bit-exact"): instances of
+// a tile sorted by depth bits, ties broken by Gaussian index -- exactly what the reference's
+// stable LSD sort of (tile<<32 | depth_bits) with values emitted in Gaussian-index order produces.
+// (depth, index) is a total order with unique keys, so ANY sorting algorithm gives the same list.
+// That freedom is what this file exploits; no global sort exists here:
 //
-// New relative to the reference: after the sort a "pack" pass gathers everything the blend
-// kernels need into one 64-byte record per instance, in sorted order, so that a tile's work list
-// is a contiguous byte range (streamed by cp.async.bulk in blend_fwd.cu / blend_bwd.cu) instead
-// of an index list that every tile has to chase through four per-Gaussian arrays.
-#include <cub/cub.cuh>
+//   1. count      bin_pass_kernel<false>: BIN_CTAS persistent CTAs, each owning one contiguous chunk of
+//                 Gaussians, histogram the tiles their rendered Gaussians touch in SHARED memory
+//                 (a warp walks one Gaussian's tile rectangle with 32 lanes) and store the
+//                 histogram as one row of a [BIN_CTAS][tiles] matrix.  No global atomics.
+//   2. offsets    column_scan_kernel: one thread per tile, exclusive prefix down the matrix column
+//                 (= where each CTA's instances of that tile start inside the tile's list) and the
+//                 tile's total.  tile_scan_kernel: one CTA, exclusive scan of the tile totals ->
+//                 tile offsets; writes the per-tile [start,end) ranges directly (no
+//                 identifyTileRanges pass, no memset), the total R and the largest tile, which the
+//                 host reads back -- the one synchronisation of the forward, as in the reference
+//                 (rasterizer_impl.cu:302).
+//   3. scatter    bin_pass_kernel<true>: same chunks, same walk; the shared-memory histogram now
+//                 starts at tile_offset + column prefix, so a shared-memory atomicAdd hands out the
+//                 final slot of the 64-bit key depth_bits<<32 | index.  Order inside a CTA's
+//                 segment is arbitrary; step 4 makes it canonical.
+//   4. sort+pack  tile_sort_pack_kernel: one CTA per tile sorts the tile's keys in shared memory
+//                 (bitonic network on 64-bit keys; a second, large-shared-memory instantiation takes
+//                 the tiles above 4096 instances, and tiles above ~25k run the same network in place in
+//                 global memory) and then writes, in sorted order, the
+//                 64-byte instance records the blend kernels stream with cp.async.bulk, plus the
+//                 sorted index list (the reference's point_list, kept for the parity tests).
+//
+// Traffic per instance: 8 B key write + 8 B read + 64 B record write (+ 64 B L2-resident record
+// read), versus ~200 B for the reference's 8-pass radix sort.
 #include "fdgs_internal.h"
 
 namespace fdgs {
-
-size_t scan_temp_bytes(int P) {
-    size_t bytes = 0;
-    cub::DeviceScan::InclusiveSum(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, P);
-    return bytes;
-}
-
-cudaError_t launch_scan(void* temp, size_t temp_bytes, const uint32_t* in, uint32_t* out, int P,
-                        cudaStream_t stream) {
-    return cub::DeviceScan::InclusiveSum(temp, temp_bytes, in, out, P, stream);
-}
-
 namespace {
 
-// reference: rasterizer_impl.cu:71-112 duplicateWithKeys
-__global__ void __launch_bounds__(256) emit_keys_kernel(int P, const float2* __restrict__ means2D,
-                                                        const float* __restrict__ depths,
-                                                        const uint32_t* __restrict__ offsets,
-                                                        const int* __restrict__ radii, int grid_x, int grid_y,
-                                                        uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
-    const int radius = radii[idx];
-    if (radius <= 0) return;
-    uint32_t off = (idx == 0) ? 0u : offsets[idx - 1];
-    const float2 p = means2D[idx];
-    int x0, y0, x1, y1;
-    get_rect(p.x, p.y, radius, grid_x, grid_y, x0, y0, x1, y1);
-    const uint64_t depth_bits = (uint64_t)__float_as_uint(depths[idx]);
-    for (int y = y0; y < y1; ++y) {
-        for (int x = x0; x < x1; ++x) {
-            const uint64_t key = ((uint64_t)(uint32_t)(y * grid_x + x) << 32) | depth_bits;
-            keys[off] = key;
-            vals[off] = (uint32_t)idx;
-            ++off;
+constexpr int BIN_CTAS = 148;      // one persistent CTA per SM; also the row count of the count matrix
+constexpr int BIN_THREADS = 1024;
+constexpr int SCAN_THREADS = 1024;
+constexpr size_t BIN_SMEM_LIMIT = 200 * 1024;
+
+// ---- 1 + 3. count / scatter ----------------------------------------------------------------------------
+// SCATTER = false: row[t] = number of (Gaussian, tile) instances of this CTA's chunk in tile t.
+// SCATTER = true : row[t] holds the column prefix on entry; keys are written to
+//                  tile_offset[t] + row[t] + (arrival order inside the CTA).
+// SMEM: histogram lives in shared memory; otherwise (very large tile grids) the CTA-private global row is used in place.
+template <bool SCATTER, bool SMEM>
+__global__ void __launch_bounds__(BIN_THREADS) bin_pass_kernel(int P, int chunk, const InstRec* __restrict__ grec,
+                                                               const int* __restrict__ radii, int grid_x, int grid_y,
+                                                               int num_tiles, uint32_t* __restrict__ matrix,
+                                                               const uint32_t* __restrict__ tile_offset,
+                                                               uint64_t* __restrict__ keys) {
+    extern __shared__ uint32_t hist_smem[];
+    uint32_t* row = matrix + (size_t)blockIdx.x * num_tiles;
+    uint32_t* hist = SMEM ? hist_smem : row;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int t = tid; t < num_tiles; t += BIN_THREADS) {
+        if (SCATTER) hist[t] = row[t] + tile_offset[t];
+        else hist[t] = 0u;
+    }
+    __syncthreads();
+    const int begin = blockIdx.x * chunk;
+    const int end = min(P, begin + chunk);
+    for (int g0 = begin + warp * 32; g0 < end; g0 += BIN_THREADS) {
+        const int idx = g0 + lane;
+        int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+        uint32_t dbits = 0;
+        bool vis = false;
+        if (idx < end) {
+            const int radius = radii[idx];
+            if (radius > 0) {
+                const float4 q0 = grec[idx].q0;   // x, y, pmin, id
+                get_rect(q0.x, q0.y, radius, grid_x, grid_y, x0, y0, x1, y1);
+                // key: depth bits (positive floats: integer order == float order) then Gaussian index
+                if (SCATTER) dbits = __float_as_uint(grec[idx].q2.w);
+                vis = true;
+            }
+        }
+        uint32_t mask = __ballot_sync(0xffffffffu, vis);
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
+            const int bx1 = __shfl_sync(0xffffffffu, x1, src), by1 = __shfl_sync(0xffffffffu, y1, src);
+            const int w = bx1 - bx0, n = w * (by1 - by0);
+            uint64_t key = 0;
+            if (SCATTER) key = ((uint64_t)__shfl_sync(0xffffffffu, dbits, src) << 32) | (uint32_t)(g0 + src);
+            for (int i = lane; i < n; i += 32) {
+                const int ry = i / w, rx = i - ry * w;
+                const int t = (by0 + ry) * grid_x + bx0 + rx;
+                const uint32_t slot = atomicAdd(&hist[t], 1u);
+                if (SCATTER) keys[slot] = key;
+            }
+        }
+    }
+    if (!SCATTER && SMEM) {
+        __syncthreads();
+        for (int t = tid; t < num_tiles; t += BIN_THREADS) row[t] = hist[t];
+    }
+}
+
+// ---- 2. offsets ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) column_scan_kernel(int num_tiles, int rows, uint32_t* __restrict__ matrix,
+                                                          uint32_t* __restrict__ tile_total) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_tiles) return;
+    uint32_t run = 0;
+    int c = 0;
+    for (; c + 4 <= rows; c += 4) {
+        uint32_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = matrix[(size_t)(c + u) * num_tiles + t];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            matrix[(size_t)(c + u) * num_tiles + t] = run;
+            run += v[u];
+        }
+    }
+    for (; c < rows; ++c) {
+        const uint32_t v = matrix[(size_t)c * num_tiles + t];
+        matrix[(size_t)c * num_tiles + t] = run;
+        run += v;
+    }
+    tile_total[t] = run;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int num_tiles, const uint32_t* __restrict__ tile_total,
+                                                                 uint32_t* __restrict__ tile_offset,
+                                                                 uint2* __restrict__ ranges, uint32_t* __restrict__ info) {
+    __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
+    __shared__ uint32_t carry;
+    __shared__ uint32_t max_count;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { carry = 0; max_count = 0; }
+    __syncthreads();
+    uint32_t my_max = 0;
+    for (int base = 0; base < num_tiles; base += SCAN_THREADS) {
+        const int t = base + tid;
+        const uint32_t c = (t < num_tiles) ? tile_total[t] : 0u;
+        my_max = max(my_max, c);
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += n;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_sums[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, w, d);
+                if (lane >= d) w += n;
+            }
+            warp_sums[lane] = w;   // inclusive over warps
+        }
+        __syncthreads();
+        const uint32_t before = carry + (warp > 0 ? warp_sums[warp - 1] : 0u) + (incl - c);
+        if (t < num_tiles) {
+            tile_offset[t] = before;
+            // empty tiles get (0,0) like the reference's memset (rasterizer_impl.cu:332)
+            ranges[t] = c ? make_uint2(before, before + c) : make_uint2(0u, 0u);
+        }
+        __syncthreads();
+        if (tid == SCAN_THREADS - 1) carry = before + c;
+        __syncthreads();
+    }
+    atomicMax(&max_count, my_max);
+    __syncthreads();
+    if (tid == 0) { info[0] = carry; info[1] = max_count; }
+}
+
+// ---- 4. per-tile sort + pack --------------------------------------------------------------------------
+constexpr int SORT_SMALL_THREADS = 256, SORT_SMALL_KEYS = 4096;      // 32 KB of keys, ~6 CTAs per SM
+constexpr int SORT_LARGE_THREADS = 1024, SORT_LARGE_KEYS = 25600;    // 200 KB of keys, 1 CTA per SM
+
+// Bitonic sorting network in its "flip" form (every sub-sequence ascending), for an arbitrary n:
+// positions >= n behave as +infinity and never move, so comparisons that would touch them are
+// simply skipped -- no padding storage, which lets oversize tiles sort in place in global memory.
+__device__ __forceinline__ void bitonic_sort(uint64_t* k, int n, int tid, int nthreads) {
+    int np = 1;
+    while (np < n) np <<= 1;
+    const int half = np >> 1;
+    for (int size = 2; size <= np; size <<= 1) {
+        __syncthreads();
+        const int hs = size >> 1, lg = __ffs(hs) - 1;
+        for (int i = tid; i < half; i += nthreads) {
+            const int blk = i >> lg, j = i & (hs - 1);
+            const int lo = blk * size + j, hi = blk * size + size - 1 - j;
+            if (hi < n) {
+                const uint64_t a = k[lo], b = k[hi];
+                if (a > b) { k[lo] = b; k[hi] = a; }
+            }
+        }
+        for (int stride = size >> 2; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int i = tid; i < half; i += nthreads) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                if (hi < n) {
+                    const uint64_t a = k[lo], b = k[hi];
+                    if (a > b) { k[lo] = b; k[hi] = a; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// Handles the tiles with n_lo < n <= n_hi; keys of tiles above CAP are sorted in place in global memory.
+template <int THREADS, int CAP>
+__global__ void __launch_bounds__(THREADS) tile_sort_pack_kernel(int n_lo, int n_hi, const uint2* __restrict__ ranges,
+                                                                 uint64_t* __restrict__ keys,
+                                                                 const InstRec* __restrict__ grec,
+                                                                 InstRec* __restrict__ recs,
+                                                                 uint32_t* __restrict__ point_list) {
+    extern __shared__ uint64_t skeys[];
+    const uint2 range = ranges[blockIdx.x];
+    const int n = (int)(range.y - range.x);
+    if (n <= n_lo || n > n_hi) return;
+    const int tid = threadIdx.x;
+    uint64_t* gk = keys + range.x;
+    const uint64_t* sorted;
+    if (n <= CAP) {
+        for (int i = tid; i < n; i += THREADS) skeys[i] = gk[i];
+        bitonic_sort(skeys, n, tid, THREADS);
+        sorted = skeys;
+    } else {
+        bitonic_sort(gk, n, tid, THREADS);
+        sorted = gk;
+    }
+    // pack: one 64-byte record per instance, in sorted order; 4 lanes copy one record (16 B each),
+    // four records in flight per lane
+    const int part = tid & 3;
+    constexpr int RPI = THREADS / 4;   // records per iteration step
+    for (int i0 = tid >> 2; i0 < n; i0 += 4 * RPI) {
+        float4 v[4];
+        uint32_t id[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * RPI;
+            if (i < n) {
+                id[u] = (uint32_t)(sorted[i] & 0xffffffffu);
+                v[u] = reinterpret_cast<const float4*>(grec + id[u])[part];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * RPI;
+            if (i < n) {
+                reinterpret_cast<float4*>(recs + range.x + i)[part] = v[u];
+                if (part == 0) point_list[range.x + i] = id[u];
+            }
         }
     }
 }
 
-__global__ void __launch_bounds__(256)
-pack_instances_kernel(int R, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ point_list,
-                      const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity,
-                      const float* __restrict__ rgb, const float* __restrict__ depths,
-                      const float* __restrict__ flows, InstRec* __restrict__ recs, uint2* __restrict__ ranges) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
-    const uint64_t key = keys[r];
-    const uint32_t tile = (uint32_t)(key >> 32);
-    // reference: rasterizer_impl.cu:117-139 identifyTileRanges
-    if (r == 0) {
-        ranges[tile].x = 0;
-    } else {
-        const uint32_t prev = (uint32_t)(keys[r - 1] >> 32);
-        if (prev != tile) {
-            ranges[prev].y = (uint32_t)r;
-            ranges[tile].x = (uint32_t)r;
-        }
+// test hook: unpack the per-Gaussian records into the reference's plain arrays; `radii` is any
+// per-Gaussian int array that is > 0 exactly for the rendered Gaussians (radii or tiles_touched)
+__global__ void unpack_grec_kernel(int P, const InstRec* __restrict__ grec, const int* __restrict__ radii,
+                                   float* depths, float* means2D, float* conic_opacity, float* rgb) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const bool vis = radii[idx] > 0;
+    const InstRec r = grec[idx];
+    if (depths) depths[idx] = vis ? r.q2.w : 0.f;
+    if (means2D) { means2D[2 * idx] = vis ? r.q0.x : 0.f; means2D[2 * idx + 1] = vis ? r.q0.y : 0.f; }
+    if (conic_opacity) {
+        conic_opacity[4 * idx + 0] = vis ? r.q1.x : 0.f; conic_opacity[4 * idx + 1] = vis ? r.q1.y : 0.f;
+        conic_opacity[4 * idx + 2] = vis ? r.q1.z : 0.f; conic_opacity[4 * idx + 3] = vis ? r.q1.w : 0.f;
     }
-    if (r == R - 1) ranges[tile].y = (uint32_t)R;
-
-    const uint32_t g = point_list[r];
-    const float2 xy = means2D[g];
-    const float4 co = conic_opacity[g];
-    const float o = co.w;
-    // Box of pixels where alpha = min(0.99, o*exp(power)) can reach 1/255 (the reference's
-    // cut-off, forward.cu:590).  Conservative: used only to SKIP work, never to change a result.
-    float ex, ey, pmin;
-    const float det = co.x * co.z - co.y * co.y;
-    if (o < 0.00392156886f) {   // alpha <= o < 1/255 everywhere: never contributes
-        ex = ey = -INFINITY;
-        pmin = INFINITY;
-    } else if (!(o <= 3.0e38f) || !(co.x > 0.f) || !(co.z > 0.f) || !(det > 0.f) || !(det <= 3.0e38f)) {
-        ex = ey = INFINITY;   // odd inputs (NaN/inf opacity, non-PD conic): no culling
-        pmin = -INFINITY;
-    } else {
-        const float qs = logf(255.0f * o) + 0.02f;   // contribute only where q(d) <= qs
-        ex = sqrtf(2.0f * qs * co.z / det) * 1.001f + 0.01f;
-        ey = sqrtf(2.0f * qs * co.x / det) * 1.001f + 0.01f;
-        pmin = -qs;
-        if (!(ex <= 3.0e38f) || !(ey <= 3.0e38f)) { ex = ey = INFINITY; pmin = -INFINITY; }
-    }
-    InstRec rec;
-    rec.q0 = make_float4(xy.x, xy.y, pmin, __uint_as_float(g));
-    rec.q1 = co;
-    rec.q2 = make_float4(rgb[3 * g + 0], rgb[3 * g + 1], rgb[3 * g + 2], depths[g]);
-    const float fx = flows ? flows[2 * g + 0] : 0.f, fy = flows ? flows[2 * g + 1] : 0.f;
-    rec.q3 = make_float4(fx, fy, ex, ey);
-    float4* dst = reinterpret_cast<float4*>(recs + r);
-    dst[0] = rec.q0;
-    dst[1] = rec.q1;
-    dst[2] = rec.q2;
-    dst[3] = rec.q3;
+    if (rgb) { rgb[3 * idx] = vis ? r.q2.x : 0.f; rgb[3 * idx + 1] = vis ? r.q2.y : 0.f; rgb[3 * idx + 2] = vis ? r.q2.z : 0.f; }
 }
 
 }  // namespace
 
-cudaError_t launch_emit_keys(int P, const float* means2D, const float* depths, const uint32_t* offsets,
-                             const int* radii, int grid_x, int grid_y, uint64_t* keys, uint32_t* vals,
-                             cudaStream_t stream) {
+int bin_ctas() { return BIN_CTAS; }
+
+template <bool SCATTER>
+static cudaError_t launch_bin_pass(int P, const InstRec* grec, const int* radii, int grid_x, int grid_y,
+                                   uint32_t* matrix, const uint32_t* tile_offset, uint64_t* keys, cudaStream_t stream) {
     if (P <= 0) return cudaSuccess;
-    emit_keys_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, reinterpret_cast<const float2*>(means2D), depths,
-                                                          offsets, radii, grid_x, grid_y, keys, vals);
+    const int num_tiles = grid_x * grid_y;
+    int chunk = (P + BIN_CTAS - 1) / BIN_CTAS;
+    chunk = (chunk + 31) & ~31;
+    const size_t smem = (size_t)num_tiles * sizeof(uint32_t);
+    if (smem <= BIN_SMEM_LIMIT) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(bin_pass_kernel<SCATTER, true>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIN_SMEM_LIMIT);
+            if (e != cudaSuccess) return e;
+            attr_set = true;
+        }
+        bin_pass_kernel<SCATTER, true><<<BIN_CTAS, BIN_THREADS, smem, stream>>>(P, chunk, grec, radii, grid_x, grid_y,
+                                                                                num_tiles, matrix, tile_offset, keys);
+    } else {
+        bin_pass_kernel<SCATTER, false><<<BIN_CTAS, BIN_THREADS, 0, stream>>>(P, chunk, grec, radii, grid_x, grid_y,
+                                                                              num_tiles, matrix, tile_offset, keys);
+    }
     return cudaGetLastError();
 }
 
-size_t sort_temp_bytes(int R) {
-    size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
-                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, R);
-    return bytes;
+cudaError_t launch_bin_count(int P, const InstRec* grec, const int* radii, int grid_x, int grid_y, uint32_t* matrix,
+                             cudaStream_t stream) {
+    if (P <= 0) return cudaMemsetAsync(matrix, 0, (size_t)BIN_CTAS * grid_x * grid_y * sizeof(uint32_t), stream);
+    return launch_bin_pass<false>(P, grec, radii, grid_x, grid_y, matrix, nullptr, nullptr, stream);
 }
 
-cudaError_t launch_sort_pairs(void* temp, size_t temp_bytes, const uint64_t* keys_in, uint64_t* keys_out,
-                              const uint32_t* vals_in, uint32_t* vals_out, int R, int end_bit,
-                              cudaStream_t stream) {
-    if (R <= 0) return cudaSuccess;
-    return cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, R, 0, end_bit,
-                                           stream);
+cudaError_t launch_tile_scan(int num_tiles, uint32_t* matrix, uint32_t* tile_total, uint32_t* tile_offset, uint2* ranges,
+                             uint32_t* info, cudaStream_t stream) {
+    column_scan_kernel<<<(num_tiles + 255) / 256, 256, 0, stream>>>(num_tiles, BIN_CTAS, matrix, tile_total);
+    tile_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(num_tiles, tile_total, tile_offset, ranges, info);
+    return cudaGetLastError();
 }
 
-cudaError_t launch_pack_instances(int R, const uint64_t* keys_sorted, const uint32_t* point_list,
-                                  const float* means2D, const float* conic_opacity, const float* rgb,
-                                  const float* depths, const float* flows, InstRec* recs, uint2* ranges,
-                                  cudaStream_t stream) {
-    if (R <= 0) return cudaSuccess;
-    pack_instances_kernel<<<(R + 255) / 256, 256, 0, stream>>>(
-        R, keys_sorted, point_list, reinterpret_cast<const float2*>(means2D),
-        reinterpret_cast<const float4*>(conic_opacity), rgb, depths, flows, recs, ranges);
+cudaError_t launch_bin_scatter(int P, const InstRec* grec, const int* radii, int grid_x, int grid_y, uint32_t* matrix,
+                               const uint32_t* tile_offset, uint64_t* keys, cudaStream_t stream) {
+    return launch_bin_pass<true>(P, grec, radii, grid_x, grid_y, matrix, tile_offset, keys, stream);
+}
+
+int tile_sort_pack_kernel_count(int max_count) { return max_count > SORT_SMALL_KEYS ? 2 : 1; }
+
+cudaError_t launch_tile_sort_pack(int num_tiles, int max_count, const uint2* ranges, uint64_t* keys, const InstRec* grec,
+                                  InstRec* recs, uint32_t* point_list, cudaStream_t stream) {
+    if (num_tiles <= 0) return cudaSuccess;
+    tile_sort_pack_kernel<SORT_SMALL_THREADS, SORT_SMALL_KEYS>
+        <<<num_tiles, SORT_SMALL_THREADS, SORT_SMALL_KEYS * sizeof(uint64_t), stream>>>(0, SORT_SMALL_KEYS, ranges, keys, grec,
+                                                                                        recs, point_list);
+    if (max_count > SORT_SMALL_KEYS) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(tile_sort_pack_kernel<SORT_LARGE_THREADS, SORT_LARGE_KEYS>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)(SORT_LARGE_KEYS * sizeof(uint64_t)));
+            if (e != cudaSuccess) return e;
+            attr_set = true;
+        }
+        tile_sort_pack_kernel<SORT_LARGE_THREADS, SORT_LARGE_KEYS>
+            <<<num_tiles, SORT_LARGE_THREADS, SORT_LARGE_KEYS * sizeof(uint64_t), stream>>>(
+                SORT_SMALL_KEYS, 0x7fffffff, ranges, keys, grec, recs, point_list);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unpack_grec(int P, const InstRec* grec, const int* radii, float* depths, float* means2D,
+                               float* conic_opacity, float* rgb, cudaStream_t stream) {
+    if (P <= 0) return cudaSuccess;
+    unpack_grec_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, grec, radii, depths, means2D, conic_opacity, rgb);
     return cudaGetLastError();
 }
 

@@ -29,7 +29,7 @@ struct __align__(128) BlendBwdSmem {
     unsigned int nmax;
 };
 
-__global__ void __launch_bounds__(BB_THREADS) blend_bwd_kernel(const BlendBwdParams p) {
+__global__ void __launch_bounds__(BB_THREADS, 3) blend_bwd_kernel(const BlendBwdParams p) {
     __shared__ BlendBwdSmem sm;
     const int tile = blockIdx.y * p.grid_x + blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -114,8 +114,9 @@ __global__ void __launch_bounds__(BB_THREADS) blend_bwd_kernel(const BlendBwdPar
                 bool rel = false;
                 if (j < cnt && (unsigned)(lo + j) < wmax) {
                     const float4 a = st[j].q0;
+                    const float4 c = st[j].q1;
                     const float4 e = st[j].q3;
-                    rel = (a.x + e.z >= bx0) && (a.x - e.z <= bx1) && (a.y + e.w >= by0) && (a.y - e.w <= by1);
+                    rel = rect_may_contribute(a.x, a.y, c.x, c.y, c.z, a.z, e.z, e.w, bx0, bx1, by0, by1);
                 }
                 uint32_t m = __ballot_sync(0xffffffffu, rel);
                 while (m) {
@@ -144,7 +145,12 @@ __global__ void __launch_bounds__(BB_THREADS) blend_bwd_kernel(const BlendBwdPar
                     if (contrib) {
                         const float4 q2 = g->q2;
                         const float4 q3 = g->q3;
-                        T = T / (1.f - alpha);
+                        // 1/(1-alpha): alpha <= 0.99, so the approximate reciprocal (1 ulp) is safe; the
+                        // reference divides twice here (backward.cu:1056,1113)
+                        const float om = 1.f - alpha;
+                        float rom;
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rom) : "f"(om));
+                        T = T * rom;
                         const float dchannel_dcolor = alpha * T;
                         // colour / flow / depth / mask recurrences, backward.cu:1062-1102
                         float dL_dalpha = (q2.x - acc_c0) * gp0 + (q2.y - acc_c1) * gp1 + (q2.z - acc_c2) * gp2;
@@ -153,7 +159,6 @@ __global__ void __launch_bounds__(BB_THREADS) blend_bwd_kernel(const BlendBwdPar
                         dL_dalpha += (1.0f - acc_m) * gm;
                         dL_dalpha *= T;
                         // accumulators as seen by the next (nearer) Gaussian
-                        const float om = 1.f - alpha;
                         acc_c0 = alpha * q2.x + om * acc_c0;
                         acc_c1 = alpha * q2.y + om * acc_c1;
                         acc_c2 = alpha * q2.z + om * acc_c2;
@@ -162,7 +167,7 @@ __global__ void __launch_bounds__(BB_THREADS) blend_bwd_kernel(const BlendBwdPar
                         acc_d = alpha * q2.w + om * acc_d;
                         acc_m = alpha + om * acc_m;
                         // background term, backward.cu:1110-1113
-                        dL_dalpha += (-T_final / om) * bg_dot_dpixel;
+                        dL_dalpha += (-T_final * rom) * bg_dot_dpixel;
 
                         const float dL_dG = q1.w * dL_dalpha;
                         const float gdx = G * dx, gdy = G * dy;

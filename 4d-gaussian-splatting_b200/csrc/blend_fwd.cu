@@ -89,8 +89,9 @@ __global__ void __launch_bounds__(BF_THREADS) blend_fwd_kernel(const BlendFwdPar
                 bool rel = false;
                 if (j < cnt) {
                     const float4 a = st[j].q0;
+                    const float4 c = st[j].q1;
                     const float4 e = st[j].q3;
-                    rel = (a.x + e.z >= bx0) && (a.x - e.z <= bx1) && (a.y + e.w >= by0) && (a.y - e.w <= by1);
+                    rel = rect_may_contribute(a.x, a.y, c.x, c.y, c.z, a.z, e.z, e.w, bx0, bx1, by0, by1);
                 }
                 uint32_t m = __ballot_sync(0xffffffffu, rel);
                 while (m) {

@@ -88,31 +88,19 @@ struct Carver {
 };
 
 struct GeomState {
-    float* depths;
-    float* means2D;
-    float* conic_opacity;
-    float* rgb;
-    float* cov3D;
-    uint8_t* clamped;
-    uint32_t* tiles_touched;
-    uint32_t* point_offsets;
-    char* scan_temp;
-    size_t scan_bytes;
+    float* cov3D;            // [P,6]  (first: exposed as covs3D_com)
+    fdgs::InstRec* grec;     // [P]    per-Gaussian 64-byte record
+    uint8_t* clamped;        // [P]
+    uint32_t* tiles_touched; // [P]
     size_t bytes;
     static GeomState carve(char* base, int P) {
         GeomState g;
         Carver c(base);
         const size_t p = (size_t)(P > 0 ? P : 0);
         g.cov3D = c.take<float>(6 * p);   // first: 128-byte aligned [P,6] view for covs3D_com
-        g.depths = c.take<float>(p);
-        g.means2D = c.take<float>(2 * p);
-        g.conic_opacity = c.take<float>(4 * p);
-        g.rgb = c.take<float>(3 * p);
+        g.grec = c.take<fdgs::InstRec>(p);
         g.clamped = c.take<uint8_t>(p);
         g.tiles_touched = c.take<uint32_t>(p);
-        g.point_offsets = c.take<uint32_t>(p);
-        g.scan_bytes = fdgs::scan_temp_bytes(P > 0 ? P : 1);
-        g.scan_temp = c.take<char>(g.scan_bytes);
         g.bytes = c.total();
         return g;
     }
@@ -121,29 +109,34 @@ struct GeomState {
 struct ImageState {
     float* final_T;
     uint32_t* n_contrib;
-    uint2* ranges;
+    uint2* ranges;           // [tiles] start/end of every tile's instance list
+    uint32_t* bin_matrix;    // [bin_ctas][tiles] per-CTA tile histograms -> column prefixes
+    uint32_t* tile_total;    // [tiles]
+    uint32_t* tile_offset;   // [tiles]
+    uint32_t* bin_info;      // [2] total instances, largest tile
+    size_t tiles;
     size_t bytes;
     static ImageState carve(char* base, int W, int H) {
         ImageState s;
         Carver c(base);
         const size_t N = (size_t)W * H;
-        const size_t tiles = (size_t)((W + fdgs::TILE_X - 1) / fdgs::TILE_X) * ((H + fdgs::TILE_Y - 1) / fdgs::TILE_Y);
+        s.tiles = (size_t)((W + fdgs::TILE_X - 1) / fdgs::TILE_X) * ((H + fdgs::TILE_Y - 1) / fdgs::TILE_Y);
         s.final_T = c.take<float>(N);
         s.n_contrib = c.take<uint32_t>(N);
-        s.ranges = c.take<uint2>(tiles);
+        s.ranges = c.take<uint2>(s.tiles);
+        s.bin_matrix = c.take<uint32_t>(s.tiles * (size_t)fdgs::bin_ctas());
+        s.tile_total = c.take<uint32_t>(s.tiles);
+        s.tile_offset = c.take<uint32_t>(s.tiles);
+        s.bin_info = c.take<uint32_t>(2);
         s.bytes = c.total();
         return s;
     }
 };
 
 struct BinningState {
-    fdgs::InstRec* recs;
-    uint32_t* point_list;
-    uint64_t* keys_sorted;
-    uint64_t* keys_unsorted;
-    uint32_t* vals_unsorted;
-    char* sort_temp;
-    size_t sort_bytes;
+    fdgs::InstRec* recs;     // [R] instance records in tile-sorted order
+    uint32_t* point_list;    // [R] sorted Gaussian indices (the reference's point_list)
+    uint64_t* keys;          // [R] depth_bits<<32 | index, grouped by tile
     size_t bytes;
     static BinningState carve(char* base, int R) {
         BinningState b;
@@ -151,11 +144,7 @@ struct BinningState {
         const size_t r = (size_t)(R > 0 ? R : 0);
         b.recs = c.take<fdgs::InstRec>(r);
         b.point_list = c.take<uint32_t>(r);
-        b.keys_sorted = c.take<uint64_t>(r);
-        b.keys_unsorted = c.take<uint64_t>(r);
-        b.vals_unsorted = c.take<uint32_t>(r);
-        b.sort_bytes = fdgs::sort_temp_bytes(R > 0 ? R : 1);
-        b.sort_temp = c.take<char>(b.sort_bytes);
+        b.keys = c.take<uint64_t>(r);
         b.bytes = c.total();
         return b;
     }
@@ -258,17 +247,25 @@ int fdgs_forward(const fdgs_forward_args* a, fdgs_alloc_fn geom_alloc, void* geo
         pp.focal_x = W / (2.0f * a->tan_fovx);
         pp.grid_x = grid_x; pp.grid_y = grid_y; pp.prefiltered = a->prefiltered;
         sh_staging(a->colors_precomp ? nullptr : a->shs, a->M, &pp.sh_bulk_ok, &pp.sh_row_stride_floats);
-        pp.out_means3D = a->out_means3D; pp.radii = a->radii; pp.means2D = geom.means2D; pp.depths = geom.depths;
-        pp.cov3D = geom.cov3D; pp.rgb = geom.rgb; pp.conic_opacity = geom.conic_opacity; pp.clamped = geom.clamped;
-        pp.tiles_touched = geom.tiles_touched;
+        pp.flows = a->flows_precomp;
+        pp.out_means3D = a->out_means3D; pp.radii = a->radii; pp.cov3D = geom.cov3D; pp.grec = geom.grec;
+        pp.clamped = geom.clamped; pp.tiles_touched = geom.tiles_touched;
         FDGS_STAGE(0, 1, fdgs::launch_preprocess_fwd(pp, stream), "preprocess_fwd");
-        FDGS_STAGE(1, 2, fdgs::launch_scan(geom.scan_temp, geom.scan_bytes, geom.tiles_touched, geom.point_offsets, P, stream),
-                   "scan");
-        // the one host synchronisation of the forward (reference: rasterizer_impl.cu:302)
-        FDGS_CUDA(cudaMemcpyAsync(&num_rendered, geom.point_offsets + (P - 1), sizeof(int), cudaMemcpyDeviceToHost, stream),
-                  "num_rendered copy");
-        FDGS_CUDA(cudaStreamSynchronize(stream), "num_rendered sync");
     }
+    // binning: per-tile counts, offsets, ranges and the total instance count R
+    FDGS_STAGE(1, (P > 0 ? 1 : 0) + 2,
+               [&]() {
+                   cudaError_t e = fdgs::launch_bin_count(P, geom.grec, a->radii, grid_x, grid_y, img.bin_matrix, stream);
+                   if (e != cudaSuccess) return e;
+                   return fdgs::launch_tile_scan((int)img.tiles, img.bin_matrix, img.tile_total, img.tile_offset, img.ranges,
+                                                 img.bin_info, stream);
+               }(),
+               "bin_count + tile_scan");
+    // the one host synchronisation of the forward (reference: rasterizer_impl.cu:302)
+    int bin_info[2] = {0, 0};
+    FDGS_CUDA(cudaMemcpyAsync(bin_info, img.bin_info, sizeof(bin_info), cudaMemcpyDeviceToHost, stream), "num_rendered copy");
+    FDGS_CUDA(cudaStreamSynchronize(stream), "num_rendered sync");
+    num_rendered = bin_info[0];
     if (num_rendered < 0) return fail(FDGS_ERR_UNSUPPORTED, "more than 2^31 tile instances");
     res->num_rendered = num_rendered;
 
@@ -279,21 +276,14 @@ int fdgs_forward(const fdgs_forward_args* a, fdgs_alloc_fn geom_alloc, void* geo
     res->binning_buffer = bin_raw;
     res->binning_bytes = bin_bytes;
 
-    FDGS_CUDA(cudaMemsetAsync(img.ranges, 0, (size_t)grid_x * grid_y * sizeof(uint2), stream), "ranges memset");
     if (num_rendered > 0) {
-        FDGS_STAGE(2, 1, fdgs::launch_emit_keys(P, geom.means2D, geom.depths, geom.point_offsets, a->radii, grid_x, grid_y,
-                                          bin.keys_unsorted, bin.vals_unsorted, stream),
-                   "emit_keys");
-        int tile_bits = 0;
-        while ((1 << tile_bits) < grid_x * grid_y) ++tile_bits;
-        FDGS_STAGE(3, 2 + (32 + tile_bits + 7) / 8, fdgs::launch_sort_pairs(bin.sort_temp, bin.sort_bytes, bin.keys_unsorted, bin.keys_sorted,
-                                           bin.vals_unsorted, bin.point_list, num_rendered, 32 + tile_bits, stream),
-                   "sort");
-        const float* colors = a->colors_precomp ? a->colors_precomp : geom.rgb;
-        FDGS_STAGE(4, 1, fdgs::launch_pack_instances(num_rendered, bin.keys_sorted, bin.point_list, geom.means2D,
-                                               geom.conic_opacity, colors, geom.depths, a->flows_precomp, bin.recs,
-                                               img.ranges, stream),
-                   "pack_instances");
+        FDGS_STAGE(2, 1, fdgs::launch_bin_scatter(P, geom.grec, a->radii, grid_x, grid_y, img.bin_matrix, img.tile_offset,
+                                                  bin.keys, stream),
+                   "bin_scatter");
+        FDGS_STAGE(3, fdgs::tile_sort_pack_kernel_count(bin_info[1]),
+                   fdgs::launch_tile_sort_pack((int)img.tiles, bin_info[1], img.ranges, bin.keys, geom.grec, bin.recs,
+                                               bin.point_list, stream),
+                   "tile_sort_pack");
     }
     fdgs::BlendFwdParams bp;
     bp.W = W; bp.H = H; bp.grid_x = grid_x; bp.grid_y = grid_y;
@@ -357,7 +347,7 @@ int fdgs_backward(const fdgs_backward_args* a, void* stream_v) {
     pb.dL_dscale = a->dL_dscale; pb.dL_dscale_t = a->dL_dscale_t; pb.dL_drot = a->dL_drot; pb.dL_drot_r = a->dL_drot_r;
     if (pb.has_scales && pb.rot_4d && (!a->rotations_r || !a->scales_t || !a->ts || !a->opacities))
         return fail(FDGS_ERR_INVALID_ARG, "rot_4d backward needs rotations_r, scales_t, ts, opacities");
-    FDGS_STAGE(7, 1, fdgs::launch_preprocess_bwd(pb, stream), "preprocess_bwd");
+    FDGS_STAGE(7, fdgs::preprocess_bwd_kernel_count(pb), fdgs::launch_preprocess_bwd(pb, stream), "preprocess_bwd");
     return FDGS_OK;
 }
 
@@ -409,11 +399,10 @@ int fdgs_debug_export_geom(const char* geom_buffer, int P, float* depths, float*
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
     GeomState g = GeomState::carve(align128(const_cast<char*>(geom_buffer)), P);
     const size_t p = (size_t)P;
-    if (depths) FDGS_CUDA(cudaMemcpyAsync(depths, g.depths, p * 4, cudaMemcpyDeviceToDevice, stream), "export depths");
-    if (means2D) FDGS_CUDA(cudaMemcpyAsync(means2D, g.means2D, p * 8, cudaMemcpyDeviceToDevice, stream), "export means2D");
-    if (conic_opacity)
-        FDGS_CUDA(cudaMemcpyAsync(conic_opacity, g.conic_opacity, p * 16, cudaMemcpyDeviceToDevice, stream), "export conic");
-    if (rgb) FDGS_CUDA(cudaMemcpyAsync(rgb, g.rgb, p * 12, cudaMemcpyDeviceToDevice, stream), "export rgb");
+    // rows the forward did not render read as zeros (their records are never written)
+    FDGS_CUDA(fdgs::launch_unpack_grec(P, g.grec, reinterpret_cast<const int*>(g.tiles_touched), depths, means2D,
+                                       conic_opacity, rgb, stream),
+              "export records");
     if (clamped) FDGS_CUDA(cudaMemcpyAsync(clamped, g.clamped, p, cudaMemcpyDeviceToDevice, stream), "export clamped");
     if (tiles_touched)
         FDGS_CUDA(cudaMemcpyAsync(tiles_touched, g.tiles_touched, p * 4, cudaMemcpyDeviceToDevice, stream), "export tiles");

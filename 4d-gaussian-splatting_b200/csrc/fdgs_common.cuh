@@ -249,6 +249,28 @@ struct __align__(16) InstRec {
 };
 static_assert(sizeof(InstRec) == 64, "InstRec must be 64 bytes");
 
+// Can the instance (centre x0,y0; conic A,B,C; pmin; slopes sbc=-B/C, sba=-B/A) contribute to any
+// pixel of the rectangle [bx0,bx1] x [by0,by1]?  It contributes at offset d only if
+// q(d) = 0.5*(A dx^2 + C dy^2) + B dx dy <= -pmin.  q is convex, so its minimum over the rectangle is
+// 0 if the centre is inside, else it lies on the edge(s) facing the centre, where it is a clamped
+// 1-D quadratic minimum.  Exact up to round-off, which the 0.02 slack inside pmin and the 1e-3 here
+// absorb; pmin = +inf means "never", pmin = -inf means "always" (irregular inputs).
+__device__ __forceinline__ bool rect_may_contribute(float x0, float y0, float A, float B, float C, float pmin,
+                                                    float sbc, float sba, float bx0, float bx1, float by0,
+                                                    float by1) {
+    const float ddx = fminf(fmaxf(x0, bx0), bx1) - x0;   // offset of the nearest rectangle point
+    const float ddy = fminf(fmaxf(y0, by0), by1) - y0;
+    // edge x = x0 + ddx, y free in the rectangle
+    const float ty = fminf(fmaxf(sbc * ddx, by0 - y0), by1 - y0);
+    const float q1 = 0.5f * (A * ddx * ddx + C * ty * ty) + B * ddx * ty;
+    // edge y = y0 + ddy, x free in the rectangle
+    const float tx = fminf(fmaxf(sba * ddy, bx0 - x0), bx1 - x0);
+    const float q2 = 0.5f * (A * tx * tx + C * ddy * ddy) + B * tx * ddy;
+    // if the centre is outside in one axis only, only that axis' edge applies; inside: q = 0
+    float qmin = (ddx != 0.f) ? ((ddy != 0.f) ? fminf(q1, q2) : q1) : ((ddy != 0.f) ? q2 : 0.f);
+    return !(qmin > -pmin + 1e-3f);   // also true for pmin = -inf, false for pmin = +inf
+}
+
 // ---- mbarrier / bulk-copy (TMA 1-D) PTX wrappers ----------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);

@@ -34,34 +34,32 @@ struct PreprocessFwdParams {
     int sh_bulk_ok;             // SH rows can be streamed with cp.async.bulk (16-byte aligned rows)
     int sh_row_stride_floats;   // padded shared-memory row stride (multiple of 4 floats)
     // outputs
+    const float* flows;     // [P,2] or NULL
     float* out_means3D;
     int* radii;
-    float* means2D;         // float2[P]
-    float* depths;
     float* cov3D;           // [P,6]
-    float* rgb;             // [P,3]
-    float* conic_opacity;   // float4[P]
+    InstRec* grec;          // [P] the 64-byte record every tile instance of the Gaussian copies
     uint8_t* clamped;       // bit ch set = channel ch was clamped at 0
     uint32_t* tiles_touched;
 };
 cudaError_t launch_preprocess_fwd(const PreprocessFwdParams& p, cudaStream_t stream);
 
 // ---- binning -----------------------------------------------------------------------------------
-size_t scan_temp_bytes(int P);
-cudaError_t launch_scan(void* temp, size_t temp_bytes, const uint32_t* in, uint32_t* out, int P,
-                        cudaStream_t stream);
-cudaError_t launch_emit_keys(int P, const float* means2D, const float* depths, const uint32_t* offsets,
-                             const int* radii, int grid_x, int grid_y, uint64_t* keys, uint32_t* vals,
+// counting sort of the (Gaussian, tile) instances by tile, BIN_CTAS persistent CTAs (binning.cu)
+int bin_ctas();                                 // rows of the [bin_ctas()][num_tiles] count matrix
+cudaError_t launch_bin_count(int P, const InstRec* grec, const int* radii, int grid_x, int grid_y, uint32_t* matrix,
                              cudaStream_t stream);
-size_t sort_temp_bytes(int R);
-cudaError_t launch_sort_pairs(void* temp, size_t temp_bytes, const uint64_t* keys_in, uint64_t* keys_out,
-                              const uint32_t* vals_in, uint32_t* vals_out, int R, int end_bit,
-                              cudaStream_t stream);
-// builds the 64-byte instance records in tile-sorted order and the per-tile [start,end) ranges
-cudaError_t launch_pack_instances(int R, const uint64_t* keys_sorted, const uint32_t* point_list,
-                                  const float* means2D, const float* conic_opacity, const float* rgb,
-                                  const float* depths, const float* flows, InstRec* recs, uint2* ranges,
-                                  cudaStream_t stream);
+// matrix -> per-CTA column prefixes; tile_offset / ranges; info[0] = total instances R, info[1] = largest tile
+cudaError_t launch_tile_scan(int num_tiles, uint32_t* matrix, uint32_t* tile_total, uint32_t* tile_offset, uint2* ranges,
+                             uint32_t* info, cudaStream_t stream);
+cudaError_t launch_bin_scatter(int P, const InstRec* grec, const int* radii, int grid_x, int grid_y, uint32_t* matrix,
+                               const uint32_t* tile_offset, uint64_t* keys, cudaStream_t stream);
+// sorts every tile's keys and writes the 64-byte instance records + the sorted index list
+int tile_sort_pack_kernel_count(int max_count);
+cudaError_t launch_tile_sort_pack(int num_tiles, int max_count, const uint2* ranges, uint64_t* keys, const InstRec* grec,
+                                  InstRec* recs, uint32_t* point_list, cudaStream_t stream);
+cudaError_t launch_unpack_grec(int P, const InstRec* grec, const int* radii, float* depths, float* means2D,
+                               float* conic_opacity, float* rgb, cudaStream_t stream);
 
 // ---- blend ---------------------------------------------------------------------------------------
 struct BlendFwdParams {
@@ -137,6 +135,7 @@ struct PreprocessBwdParams {
     float* dL_drot_r;
 };
 cudaError_t launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream);
+int preprocess_bwd_kernel_count(const PreprocessBwdParams& p);
 
 cudaError_t launch_mark_visible(int P, const float* means3D, const float* viewmatrix, unsigned char* present,
                                 cudaStream_t stream);

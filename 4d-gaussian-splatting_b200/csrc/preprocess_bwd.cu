@@ -1,28 +1,37 @@
-// preprocess_bwd.cu -- per-Gaussian backward preprocessing (one thread per Gaussian).
+// preprocess_bwd.cu -- per-Gaussian backward preprocessing.
 //
-// Fuses the reference's two backward preprocessing kernels -- computeCov2DCUDA
+// Replaces the reference's two backward preprocessing kernels -- computeCov2DCUDA
 // (backward.cu:486-617) and preprocessCUDA<3> (backward.cu:839-923) with its helpers
 // computeColorFromSH (:20-139), computeColorFromSH_4D (:144-481), computeCov3D (:621-684),
-// computeCov3D_conditional (:689-834) -- into one pass, so dL_dcov3D / dL_dmeans never make a
-// round trip through HBM between them.
+// computeCov3D_conditional (:689-834).  Two kernels here, split by what bounds them:
 //
-// B200 design:
-//   * every output row is written by this kernel (zeros for Gaussians that were not rendered), so
-//     the host never zero-fills the eight parameter-gradient tensors (the reference memsets
-//     716 B per Gaussian first, rasterize_points.cu:201-213);
-//   * SH rows (12*M bytes) are streamed in with cp.async.bulk like the forward, and the
-//     12*M-byte dL_dsh rows are staged in the same shared-memory rows and written out by the whole
-//     CTA as fully coalesced 16-byte stores (the reference writes 12-byte pieces at a 12*M-byte
-//     stride per thread).
+//   sh_bwd_kernel    HBM-bound.  Reads the 12*M-byte SH row of every rendered Gaussian and writes
+//                    the 12*M-byte dL_dsh row of EVERY Gaussian (zeros where not rendered, so the
+//                    host never memsets the 1.15 GB tensor; reference: rasterize_points.cu:209).
+//                    Rows move with cp.async.bulk in both directions (global->shared on an
+//                    mbarrier, shared->global as a bulk group); in shared memory a row is read and
+//                    overwritten in place with conflict-free 128-bit accesses; only rendered rows
+//                    occupy shared memory (block-level compaction), which keeps 5 CTAs per SM
+//                    resident; zero rows are written with coalesced 16-byte stores.
+//   geom_bwd_kernel  latency/ALU-bound.  Fuses computeCov2DCUDA with the projection and the
+//                    3D / conditional-4D covariance chains, so dL_dcov3D and dL_dmeans never make
+//                    a round trip through HBM; writes every row of the seven parameter-gradient
+//                    tensors (zeros where not rendered; reference memsets them first,
+//                    rasterize_points.cu:201-213).
+//
 // Bug-compatible with the reference where the bugs are observable:
 // dL_dsh[1] uses l0m0 in the 4D variant (backward.cu:190), the temporal derivative has no minus
-// sign (:303,:384) and is overwritten, not accumulated, for deg_t > 1 (:403).
+// sign (:303,:384) and is overwritten, not accumulated, for deg_t > 1 (:403); the SH view
+// direction is taken from the SHIFTED mean here (rasterizer_impl.cu:463) although the forward
+// used the unshifted one.
 #include "fdgs_internal.h"
 
 namespace fdgs {
 namespace {
 
-constexpr int PB_THREADS = 128;
+constexpr int SB_THREADS = 128;   // SH kernel: Gaussians per CTA
+constexpr int SB_CAP = 64;        // shared-memory row slots per CTA (rendered rows per round)
+constexpr int GB_THREADS = 128;   // geometry kernel
 
 __device__ __forceinline__ float3 dnormvdv3(float3 v, float3 dv) {   // auxiliary.h:108-118
     const float sum2 = v.x * v.x + v.y * v.y + v.z * v.z;
@@ -79,7 +88,221 @@ __device__ __forceinline__ void sh_basis_deriv(float x, float y, float z, int de
     }
 }
 
-// 4x4 helpers, glm convention: A[c][r], (A*B)[c][r] = sum_k A[k][r] * B[c][k]
+// per-Gaussian constants of the SH backward
+struct ShCtx {
+    ShDeriv SD;
+    float dRGB[3];
+    float3 dir_orig;
+    float tw[3], dtw[3];   // temporal weight / its (reference-style) derivative per 16-coefficient block
+    int nblk;              // active blocks: 1 (spatial) .. 3
+    int ncoef;             // active coefficients per block: (D+1)^2
+    bool sh4d;
+};
+
+__device__ __forceinline__ void sh_ctx_init(const PreprocessBwdParams& a, int idx, ShCtx& c) {
+    c.sh4d = !((a.gaussian_dim == 3) || a.force_sh_3d);
+    const unsigned cl = a.clamped[idx];
+    c.dRGB[0] = (cl & 1u) ? 0.f : a.dL_dcolor[3 * idx + 0];
+    c.dRGB[1] = (cl & 2u) ? 0.f : a.dL_dcolor[3 * idx + 1];
+    c.dRGB[2] = (cl & 4u) ? 0.f : a.dL_dcolor[3 * idx + 2];
+    const float mx = a.means3D[3 * idx + 0], my = a.means3D[3 * idx + 1], mz = a.means3D[3 * idx + 2];
+    c.dir_orig = make_float3(mx - a.campos[0], my - a.campos[1], mz - a.campos[2]);
+    const float len = sqrtf(c.dir_orig.x * c.dir_orig.x + c.dir_orig.y * c.dir_orig.y + c.dir_orig.z * c.dir_orig.z);
+    sh_basis_deriv(c.dir_orig.x / len, c.dir_orig.y / len, c.dir_orig.z / len, a.D, c.SD);
+    c.ncoef = (a.D + 1) * (a.D + 1);
+    c.tw[0] = 1.f; c.tw[1] = c.tw[2] = 0.f;
+    c.dtw[0] = c.dtw[1] = c.dtw[2] = 0.f;
+    c.nblk = 1;
+    if (c.sh4d && a.D > 2 && a.D_t > 0) {
+        const float dir_t = a.ts[idx] - a.timestamp;
+        const double w = 2 * FDGS_MY_PI * (double)dir_t / (double)a.time_duration;
+        c.tw[1] = (float)cos(w);
+        c.dtw[1] = (float)(sin(w) * 2 * FDGS_MY_PI / (double)a.time_duration);
+        c.nblk = 2;
+        if (a.D_t > 1) {
+            const double w2 = 2 * FDGS_MY_PI * (double)dir_t * 2 / (double)a.time_duration;
+            c.tw[2] = (float)cos(w2);
+            c.dtw[2] = (float)(sin(w2) * 2 * FDGS_MY_PI * 2 / (double)a.time_duration);
+            c.nblk = 3;
+        }
+    }
+}
+
+// Consumes the SH row held in `rowq` (float4, in place) and replaces it by the dL_dsh row.
+// Returns the direction sums and the temporal term.  NQ = number of float4 in the row (3*M/4).
+__device__ __forceinline__ void sh_row_inplace(float4* rowq, int nq, const ShCtx& c, float& ddx, float& ddy,
+                                               float& ddz, float& dtt) {
+    ddx = ddy = ddz = dtt = 0.f;
+    const int ngroups = nq / 3;   // groups of 4 coefficients
+#pragma unroll
+    for (int blk = 0; blk < 3; ++blk) {
+        if (blk * 4 >= ngroups) break;
+        const bool blk_on = blk < c.nblk;
+        float sx = 0.f, sy = 0.f, sz = 0.f, sl = 0.f;
+#pragma unroll
+        for (int kg = 0; kg < 4; ++kg) {
+            const int G = blk * 4 + kg;
+            if (G >= ngroups) break;
+            float4 q[3];
+            float f[12];
+            const bool grp_on = blk_on && (kg * 4 < c.ncoef);
+            if (grp_on) {
+                q[0] = rowq[3 * G + 0]; q[1] = rowq[3 * G + 1]; q[2] = rowq[3 * G + 2];
+                f[0] = q[0].x; f[1] = q[0].y; f[2] = q[0].z; f[3] = q[0].w;
+                f[4] = q[1].x; f[5] = q[1].y; f[6] = q[1].z; f[7] = q[1].w;
+                f[8] = q[2].x; f[9] = q[2].y; f[10] = q[2].z; f[11] = q[2].w;
+            }
+            float o[12];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = kg * 4 + j;
+                float w = 0.f;
+                if (grp_on && k < c.ncoef) {
+                    const float sk = f[3 * j] * c.dRGB[0] + f[3 * j + 1] * c.dRGB[1] + f[3 * j + 2] * c.dRGB[2];
+                    sx += c.SD.dx[k] * sk;
+                    sy += c.SD.dy[k] * sk;
+                    sz += c.SD.dz[k] * sk;
+                    sl += c.SD.l[k] * sk;
+                    // dL_dsh[1] = l0m0 * dL_dRGB in the 4D variant (quirk, backward.cu:190)
+                    w = (blk == 0) ? ((c.sh4d && k == 1) ? c.SD.l[0] : c.SD.l[k]) : c.tw[blk] * c.SD.l[k];
+                }
+                o[3 * j + 0] = w * c.dRGB[0];
+                o[3 * j + 1] = w * c.dRGB[1];
+                o[3 * j + 2] = w * c.dRGB[2];
+            }
+            rowq[3 * G + 0] = make_float4(o[0], o[1], o[2], o[3]);
+            rowq[3 * G + 1] = make_float4(o[4], o[5], o[6], o[7]);
+            rowq[3 * G + 2] = make_float4(o[8], o[9], o[10], o[11]);
+        }
+        if (blk_on) {
+            ddx += c.tw[blk] * sx;
+            ddy += c.tw[blk] * sy;
+            ddz += c.tw[blk] * sz;
+            if (blk > 0) dtt = c.dtw[blk] * sl;   // overwrites: backward.cu:403
+        }
+    }
+    // coefficients beyond the three 16-blocks (M > 48) are never used: zero gradient
+    for (int qi = 36; qi < nq; ++qi) rowq[qi] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// ---- SH backward ----------------------------------------------------------------------------------
+template <bool BULK>
+__global__ void __launch_bounds__(SB_THREADS, 4) sh_bwd_kernel(const PreprocessBwdParams a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ short slot_of[SB_THREADS];   // rank among the rendered rows of this CTA, -1 = not rendered
+    __shared__ int warp_cnt[SB_THREADS / 32];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int idx = blockIdx.x * SB_THREADS + tid;
+    const bool in_range = idx < a.P;
+    const bool vis = in_range && (a.radii[idx] > 0) && (a.tiles_touched[idx] != 0u);
+    const int row_floats = 3 * a.M;
+    const int nq = row_floats / 4;
+
+    // block-level compaction of the rendered rows
+    const unsigned bal = __ballot_sync(0xffffffffu, vis);
+    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    if (BULK && tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    int base = 0, nvis = 0;
+#pragma unroll
+    for (int w = 0; w < SB_THREADS / 32; ++w) {
+        if (w < warp) base += warp_cnt[w];
+        nvis += warp_cnt[w];
+    }
+    const int my_rank = vis ? base + __popc(bal & ((1u << lane) - 1u)) : -1;
+    slot_of[tid] = (short)my_rank;
+    __syncthreads();
+
+    // zero rows: every float4 of every non-rendered row of this CTA, coalesced
+    {
+        const int rows_here = min(SB_THREADS, a.P - blockIdx.x * SB_THREADS);
+        float4* dst = reinterpret_cast<float4*>(a.dL_dsh + (size_t)blockIdx.x * SB_THREADS * row_floats);
+        const int total = rows_here * nq;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (BULK) {
+            for (int f = tid; f < total; f += SB_THREADS) {
+                const int r = f / nq;
+                if (slot_of[r] < 0) dst[f] = z;
+            }
+        } else {
+            // generic path (row not a multiple of 16 bytes): scalar stores
+            float* d1 = a.dL_dsh + (size_t)blockIdx.x * SB_THREADS * row_floats;
+            for (int f = tid; f < rows_here * row_floats; f += SB_THREADS)
+                if (slot_of[f / row_floats] < 0) d1[f] = 0.f;
+        }
+    }
+
+    ShCtx c;
+    if (vis) sh_ctx_init(a, idx, c);
+
+    if (BULK) {
+        float* rows = reinterpret_cast<float*>(smem_raw);
+        for (int round = 0, lo = 0; lo < nvis; ++round, lo += SB_CAP) {
+            const int cnt = min(SB_CAP, nvis - lo);
+            const bool mine = vis && my_rank >= lo && my_rank < lo + cnt;
+            float4* rowq = reinterpret_cast<float4*>(rows + (size_t)(my_rank - lo) * a.sh_row_stride_floats);
+            if (round > 0) {
+                // the previous round's bulk stores must have finished reading the slots
+                if (vis) bulk_wait_read_all();
+                __syncthreads();
+            }
+            if (tid == 0) mbar_expect_tx(&bar, (uint32_t)cnt * (uint32_t)row_floats * 4u);
+            if (mine) bulk_g2s(rowq, a.shs + (size_t)idx * row_floats, (uint32_t)row_floats * 4u, &bar);
+            if (mine) {
+                mbar_wait(&bar, (uint32_t)round & 1u);
+                float ddx, ddy, ddz, dtt;
+                sh_row_inplace(rowq, nq, c, ddx, ddy, ddz, dtt);
+                fence_async_smem();
+                bulk_s2g(a.dL_dsh + (size_t)idx * row_floats, rowq, (uint32_t)row_floats * 4u);
+                bulk_commit();
+                const float3 dm = dnormvdv3(c.dir_orig, make_float3(ddx, ddy, ddz));
+                a.dL_dmean3D[3 * idx + 0] = dm.x;
+                a.dL_dmean3D[3 * idx + 1] = dm.y;
+                a.dL_dmean3D[3 * idx + 2] = dm.z;
+                a.dL_dts[idx] = c.sh4d ? dtt : 0.f;
+            }
+        }
+        if (vis) bulk_wait_all();
+    } else if (vis) {
+        // generic path: global loads / stores, one coefficient at a time
+        const float* grow = a.shs + (size_t)idx * row_floats;
+        float* drow = a.dL_dsh + (size_t)idx * row_floats;
+        float ddx = 0.f, ddy = 0.f, ddz = 0.f, dtt = 0.f;
+        for (int blk = 0; blk * 16 < a.M; ++blk) {
+            float sx = 0.f, sy = 0.f, sz = 0.f, sl = 0.f;
+            const bool blk_on = blk < c.nblk;
+            for (int k = 0; k < 16 && blk * 16 + k < a.M; ++k) {
+                const int cidx = blk * 16 + k;
+                float w = 0.f;
+                if (blk_on && k < c.ncoef) {
+                    const float sk = __ldg(grow + 3 * cidx) * c.dRGB[0] + __ldg(grow + 3 * cidx + 1) * c.dRGB[1] +
+                                     __ldg(grow + 3 * cidx + 2) * c.dRGB[2];
+                    sx += c.SD.dx[k] * sk; sy += c.SD.dy[k] * sk; sz += c.SD.dz[k] * sk; sl += c.SD.l[k] * sk;
+                    w = (blk == 0) ? ((c.sh4d && k == 1) ? c.SD.l[0] : c.SD.l[k]) : c.tw[blk < 3 ? blk : 0] * c.SD.l[k];
+                }
+                drow[3 * cidx + 0] = w * c.dRGB[0];
+                drow[3 * cidx + 1] = w * c.dRGB[1];
+                drow[3 * cidx + 2] = w * c.dRGB[2];
+            }
+            if (blk_on) {
+                ddx += c.tw[blk] * sx; ddy += c.tw[blk] * sy; ddz += c.tw[blk] * sz;
+                if (blk > 0) dtt = c.dtw[blk] * sl;
+            }
+        }
+        const float3 dm = dnormvdv3(c.dir_orig, make_float3(ddx, ddy, ddz));
+        a.dL_dmean3D[3 * idx + 0] = dm.x;
+        a.dL_dmean3D[3 * idx + 1] = dm.y;
+        a.dL_dmean3D[3 * idx + 2] = dm.z;
+        a.dL_dts[idx] = c.sh4d ? dtt : 0.f;
+    }
+}
+
+// 4x4 / 3x3 helpers, glm convention: A[c][r], (A*B)[c][r] = sum_k A[k][r] * B[c][k]
 __device__ __forceinline__ void mat4_mul(const float A[4][4], const float B[4][4], float C[4][4]) {
 #pragma unroll
     for (int c = 0; c < 4; ++c)
@@ -87,9 +310,6 @@ __device__ __forceinline__ void mat4_mul(const float A[4][4], const float B[4][4
         for (int r = 0; r < 4; ++r)
             C[c][r] = A[0][r] * B[c][0] + A[1][r] * B[c][1] + A[2][r] * B[c][2] + A[3][r] * B[c][3];
 }
-
-
-// 3x3 helpers, same convention
 __device__ __forceinline__ void mat3_mul(const float A[3][3], const float B[3][3], float C[3][3]) {
 #pragma unroll
     for (int c = 0; c < 3; ++c)
@@ -97,44 +317,23 @@ __device__ __forceinline__ void mat3_mul(const float A[3][3], const float B[3][3
         for (int r = 0; r < 3; ++r) C[c][r] = A[0][r] * B[c][0] + A[1][r] * B[c][1] + A[2][r] * B[c][2];
 }
 
-template <bool BULK>
-__global__ void __launch_bounds__(PB_THREADS) preprocess_bwd_kernel(const PreprocessBwdParams a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ unsigned char row_live[PB_THREADS];
+// ---- geometry backward ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(GB_THREADS) geom_bwd_kernel(const PreprocessBwdParams a, const int has_sh_part) {
+    const int idx = blockIdx.x * GB_THREADS + threadIdx.x;
+    if (idx >= a.P) return;
+    const bool vis = (a.radii[idx] > 0) && (a.tiles_touched[idx] != 0u);
 
-    const int idx = blockIdx.x * PB_THREADS + threadIdx.x;
-    const bool in_range = idx < a.P;
-    const bool vis = in_range && (a.radii[idx] > 0) && (a.tiles_touched[idx] != 0u);
-    const int row_floats = 3 * a.M;
-    const bool has_sh = (a.shs != nullptr) && a.M > 0;
-    float* my_row = reinterpret_cast<float*>(smem_raw) + (size_t)threadIdx.x * a.sh_row_stride_floats;
-
-    if (BULK) {
-        if (threadIdx.x == 0) {
-            mbar_init(&bar, 1);
-            mbar_fence_init();
-        }
-        row_live[threadIdx.x] = vis ? 1 : 0;
-        const int nvis = __syncthreads_count(vis);
-        if (threadIdx.x == 0 && nvis > 0) mbar_expect_tx(&bar, (uint32_t)nvis * (uint32_t)row_floats * 4u);
-        if (vis) bulk_g2s(my_row, a.shs + (size_t)idx * row_floats, (uint32_t)row_floats * 4u, &bar);
-    }
-
-    // gradients produced for this Gaussian (zeros unless rendered)
     float g_mean[3] = {0.f, 0.f, 0.f};
     float g_cov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float g_ts = 0.f, g_scale[3] = {0.f, 0.f, 0.f}, g_scale_t = 0.f;
     float g_rot[4] = {0.f, 0.f, 0.f, 0.f}, g_rotr[4] = {0.f, 0.f, 0.f, 0.f};
-    float dRGB[3] = {0.f, 0.f, 0.f};
-    float tw1 = 0.f, tw2 = 0.f;   // temporal weights of SH blocks 1 and 2 (0 = block inactive)
-    ShDeriv SD;
-    bool sh4d = false;
 
     if (vis) {
         const float* V = a.viewmatrix;
         const float mx = a.means3D[3 * idx + 0], my = a.means3D[3 * idx + 1], mz = a.means3D[3 * idx + 2];
-        const float* c3 = a.cov3D + 6 * idx;
+        float c3[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) c3[i] = a.cov3D[6 * idx + i];
 
         // ---------------- computeCov2DCUDA, backward.cu:486-617 ----------------
         {
@@ -206,65 +405,12 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_bwd_kernel(const Prepro
             g_mean[2] += (Pm[8] * m_w - Pm[11] * mul1) * d2x + (Pm[9] * m_w - Pm[11] * mul2) * d2y;
         }
 
-        // ---------------- SH backward, backward.cu:20-139 / :144-481 ----------------
-        if (has_sh) {
-            sh4d = !((a.gaussian_dim == 3) || a.force_sh_3d);
-            const unsigned cl = a.clamped[idx];
-            dRGB[0] = (cl & 1u) ? 0.f : a.dL_dcolor[3 * idx + 0];
-            dRGB[1] = (cl & 2u) ? 0.f : a.dL_dcolor[3 * idx + 1];
-            dRGB[2] = (cl & 4u) ? 0.f : a.dL_dcolor[3 * idx + 2];
-            const float3 dir_orig = make_float3(mx - a.campos[0], my - a.campos[1], mz - a.campos[2]);
-            const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
-            const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
-            sh_basis_deriv(x, y, z, a.D, SD);
-            float dt1_dt = 0.f, dt2_dt = 0.f;
-            if (sh4d && a.D > 2 && a.D_t > 0) {
-                const float dir_t = a.ts[idx] - a.timestamp;
-                const double w = 2 * FDGS_MY_PI * (double)dir_t / (double)a.time_duration;
-                tw1 = (float)cos(w);
-                dt1_dt = (float)(sin(w) * 2 * FDGS_MY_PI / (double)a.time_duration);
-                if (a.D_t > 1) {
-                    const double w2 = 2 * FDGS_MY_PI * (double)dir_t * 2 / (double)a.time_duration;
-                    tw2 = (float)cos(w2);
-                    dt2_dt = (float)(sin(w2) * 2 * FDGS_MY_PI * 2 / (double)a.time_duration);
-                }
-            }
-            const bool blk1 = sh4d && a.D > 2 && a.D_t > 0, blk2 = blk1 && a.D_t > 1;
-            if (BULK) mbar_wait(&bar, 0);
-            // s_k = sh[k] . dL_dRGB ; direction / time gradients are weighted sums of s_k
-            float ddx = 0.f, ddy = 0.f, ddz = 0.f, dtt = 0.f;
-            const float* grow = a.shs + (size_t)idx * row_floats;
-            const int ncoef = (a.D + 1) * (a.D + 1);
-#pragma unroll 1
-            for (int blk = 0; blk < 3; ++blk) {
-                if (blk == 1 && !blk1) break;
-                if (blk == 2 && !blk2) break;
-                const float twt = (blk == 0) ? 1.f : (blk == 1 ? tw1 : tw2);
-                float sx = 0.f, sy = 0.f, sz = 0.f, sl = 0.f;
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    if (k >= ncoef) break;
-                    const int c = blk * 16 + k;
-                    float s0, s1, s2;
-                    if (BULK) { s0 = my_row[3 * c + 0]; s1 = my_row[3 * c + 1]; s2 = my_row[3 * c + 2]; }
-                    else { s0 = __ldg(grow + 3 * c + 0); s1 = __ldg(grow + 3 * c + 1); s2 = __ldg(grow + 3 * c + 2); }
-                    const float sk = s0 * dRGB[0] + s1 * dRGB[1] + s2 * dRGB[2];
-                    sx += SD.dx[k] * sk;
-                    sy += SD.dy[k] * sk;
-                    sz += SD.dz[k] * sk;
-                    sl += SD.l[k] * sk;
-                }
-                ddx += twt * sx;
-                ddy += twt * sy;
-                ddz += twt * sz;
-                if (blk == 1) dtt = dt1_dt * sl;
-                if (blk == 2) dtt = dt2_dt * sl;   // overwrites (backward.cu:403)
-            }
-            const float3 dm = dnormvdv3(dir_orig, make_float3(ddx, ddy, ddz));
-            g_mean[0] += dm.x;
-            g_mean[1] += dm.y;
-            g_mean[2] += dm.z;
-            if (sh4d) g_ts += dtt;
+        // SH view-direction / time terms left by sh_bwd_kernel (backward.cu:896-906)
+        if (has_sh_part) {
+            g_mean[0] += a.dL_dmean3D[3 * idx + 0];
+            g_mean[1] += a.dL_dmean3D[3 * idx + 1];
+            g_mean[2] += a.dL_dmean3D[3 * idx + 2];
+            g_ts += a.dL_dts[idx];
         }
 
         // ---------------- covariance backward ----------------
@@ -326,7 +472,7 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_bwd_kernel(const Prepro
 #pragma unroll
                         for (int r = 0; r < 4; ++r) M2[c][r] = 2.0f * S.M[c][r];
                     mat4_mul(M2, dS, dM);   // dL_dM = 2 * M * dL_dSigma
-                    // dL_dscale_i = sum_c R[c][i] * dL_dM[c][i],  R = M / s
+                    // dL_dscale_i = sum_c R[c][i] * dL_dM[c][i]
                     float N[4][4];   // N[i][j] = s_i * dL_dM[j][i]   (= scaled dL_dMt)
                     float gs[4];
 #pragma unroll
@@ -396,91 +542,19 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_bwd_kernel(const Prepro
         }
     }
 
-    // ---------------- outputs: every row of every overwritten tensor ----------------
-    if (in_range) {
+    // every row of every overwritten tensor
 #pragma unroll
-        for (int i = 0; i < 3; ++i) a.dL_dmean3D[3 * idx + i] = g_mean[i];
+    for (int i = 0; i < 3; ++i) a.dL_dmean3D[3 * idx + i] = g_mean[i];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) a.dL_dcov3D[6 * idx + i] = g_cov[i];
-        a.dL_dts[idx] = g_ts;
+    for (int i = 0; i < 6; ++i) a.dL_dcov3D[6 * idx + i] = g_cov[i];
+    a.dL_dts[idx] = g_ts;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) a.dL_dscale[3 * idx + i] = g_scale[i];
-        a.dL_dscale_t[idx] = g_scale_t;
-        reinterpret_cast<float4*>(a.dL_drot)[idx] = make_float4(g_rot[0], g_rot[1], g_rot[2], g_rot[3]);
-        reinterpret_cast<float4*>(a.dL_drot_r)[idx] = make_float4(g_rotr[0], g_rotr[1], g_rotr[2], g_rotr[3]);
-    }
-
-    if (a.dL_dsh != nullptr && a.M > 0) {
-        // dL_dsh[k] = weight_k * dL_dRGB; weight 0 beyond the active degree
-        const int ncoef = (a.D + 1) * (a.D + 1);
-        auto weight = [&](int c) -> float {
-            const int blk = c >> 4, k = c & 15;
-            if (!vis || k >= ncoef || c >= a.M) return 0.f;
-            if (blk == 0) return (sh4d && k == 1) ? SD.l[0] : SD.l[k];   // quirk: backward.cu:190
-            if (!sh4d || !(a.D > 2)) return 0.f;
-            if (blk == 1) return (a.D_t > 0) ? tw1 * SD.l[k] : 0.f;
-            if (blk == 2) return (a.D_t > 1) ? tw2 * SD.l[k] : 0.f;
-            return 0.f;
-        };
-        if (BULK) {
-            // stage my row in shared memory (all lanes: zeros if not rendered), then the CTA writes the
-            // contiguous [rows_in_block, 3M] slab with coalesced 16-byte stores
-            if (vis && has_sh) {
-                for (int c = 0; c < a.M; ++c) {
-                    const float w = weight(c);
-                    my_row[3 * c + 0] = w * dRGB[0];
-                    my_row[3 * c + 1] = w * dRGB[1];
-                    my_row[3 * c + 2] = w * dRGB[2];
-                }
-            }
-            __syncthreads();
-            const int rows_here = min(PB_THREADS, a.P - blockIdx.x * PB_THREADS);
-            const int q_per_row = row_floats / 4;
-            float4* dst = reinterpret_cast<float4*>(a.dL_dsh + (size_t)blockIdx.x * PB_THREADS * row_floats);
-            const int total = rows_here * q_per_row;
-            for (int f = threadIdx.x; f < total; f += PB_THREADS) {
-                const int r = f / q_per_row, q = f - r * q_per_row;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row_live[r])
-                    v = reinterpret_cast<const float4*>(reinterpret_cast<float*>(smem_raw) +
-                                                        (size_t)r * a.sh_row_stride_floats)[q];
-                dst[f] = v;
-            }
-        } else if (in_range) {
-            float* drow = a.dL_dsh + (size_t)idx * row_floats;
-            for (int c = 0; c < a.M; ++c) {
-                const float w = (vis && has_sh) ? weight(c) : 0.f;
-                drow[3 * c + 0] = w * dRGB[0];
-                drow[3 * c + 1] = w * dRGB[1];
-                drow[3 * c + 2] = w * dRGB[2];
-            }
-        }
-    }
+    for (int i = 0; i < 3; ++i) a.dL_dscale[3 * idx + i] = g_scale[i];
+    a.dL_dscale_t[idx] = g_scale_t;
+    reinterpret_cast<float4*>(a.dL_drot)[idx] = make_float4(g_rot[0], g_rot[1], g_rot[2], g_rot[3]);
+    reinterpret_cast<float4*>(a.dL_drot_r)[idx] = make_float4(g_rotr[0], g_rotr[1], g_rotr[2], g_rotr[3]);
 }
 
-}  // namespace
-
-cudaError_t launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream) {
-    if (p.P <= 0) return cudaSuccess;
-    const int blocks = (p.P + PB_THREADS - 1) / PB_THREADS;
-    const bool bulk = p.sh_bulk_ok && p.shs != nullptr && p.M > 0 && p.dL_dsh != nullptr;
-    if (bulk) {
-        const size_t smem = (size_t)PB_THREADS * p.sh_row_stride_floats * sizeof(float);
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(preprocess_bwd_kernel<true>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            if (e != cudaSuccess) return e;
-            attr_set = true;
-        }
-        preprocess_bwd_kernel<true><<<blocks, PB_THREADS, smem, stream>>>(p);
-    } else {
-        preprocess_bwd_kernel<false><<<blocks, PB_THREADS, 0, stream>>>(p);
-    }
-    return cudaGetLastError();
-}
-
-namespace {
 // reference: rasterizer_impl.cu:54-67 checkFrustum + auxiliary.h:140-163
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means, const float* __restrict__ V,
                                     unsigned char* __restrict__ present) {
@@ -489,7 +563,37 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means, cons
     const float z = xform_row(V[2], V[6], V[10], V[14], means[3 * idx], means[3 * idx + 1], means[3 * idx + 2]);
     present[idx] = (z <= 0.2f) ? 0 : 1;
 }
+
 }  // namespace
+
+int preprocess_bwd_kernel_count(const PreprocessBwdParams& p) {
+    return (p.shs != nullptr && p.M > 0 && p.dL_dsh != nullptr) ? 2 : 1;
+}
+
+cudaError_t launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream) {
+    if (p.P <= 0) return cudaSuccess;
+    const bool has_sh = p.shs != nullptr && p.M > 0 && p.dL_dsh != nullptr;
+    if (has_sh) {
+        const int blocks = (p.P + SB_THREADS - 1) / SB_THREADS;
+        if (p.sh_bulk_ok) {
+            const size_t smem = (size_t)SB_CAP * p.sh_row_stride_floats * sizeof(float);
+            static bool attr_set = false;
+            if (!attr_set) {
+                cudaError_t e = cudaFuncSetAttribute(sh_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     200 * 1024);
+                if (e != cudaSuccess) return e;
+                attr_set = true;
+            }
+            sh_bwd_kernel<true><<<blocks, SB_THREADS, smem, stream>>>(p);
+        } else {
+            sh_bwd_kernel<false><<<blocks, SB_THREADS, 0, stream>>>(p);
+        }
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    geom_bwd_kernel<<<(p.P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, stream>>>(p, has_sh ? 1 : 0);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_mark_visible(int P, const float* means3D, const float* viewmatrix, unsigned char* present,
                                 cudaStream_t stream) {

@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const Prepr
     float conx = 0.f, cony = 0.f, conz = 0.f;
     int radius = 0;
     uint32_t tiles = 0;
+    int rx0 = 0, ry0 = 0, rx1 = 0, ry1 = 0;   // tile rectangle
     float mx = 0.f, my = 0.f, mz = 0.f;   // (shifted) mean
     float ox = 0.f, oy = 0.f, oz = 0.f;   // original mean (SH view direction, quirk: forward.cu:480,482)
 
@@ -297,9 +298,8 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const Prepr
                     px = ndc2pix(projx, a.W);
                     py = ndc2pix(projy, a.H);
                     radius = (int)my_radius;
-                    int x0, y0, x1, y1;
-                    get_rect(px, py, radius, a.grid_x, a.grid_y, x0, y0, x1, y1);
-                    tiles = (uint32_t)((x1 - x0) * (y1 - y0));
+                    get_rect(px, py, radius, a.grid_x, a.grid_y, rx0, ry0, rx1, ry1);
+                    tiles = (uint32_t)((rx1 - rx0) * (ry1 - ry0));
                     if (tiles == 0 || radius < 1) alive = false;
                 }
             }
@@ -355,13 +355,32 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const Prepr
         a.radii[idx] = visible ? radius : 0;
         a.tiles_touched[idx] = visible ? tiles : 0u;
         if (visible) {
-            a.depths[idx] = depth;
-            reinterpret_cast<float2*>(a.means2D)[idx] = make_float2(px, py);
-            reinterpret_cast<float4*>(a.conic_opacity)[idx] = make_float4(conx, cony, conz, opacity);
-            a.rgb[3 * idx + 0] = rgb[0];
-            a.rgb[3 * idx + 1] = rgb[1];
-            a.rgb[3 * idx + 2] = rgb[2];
             a.clamped[idx] = clamp_bits;
+            // The 64-byte record every (tile, Gaussian) instance copies (binning.cu).  Besides the
+            // reference's means2D / conic_opacity / rgb / depth it carries the culling data of the
+            // blend kernels: the Gaussian can only contribute where alpha = min(0.99, o*exp(power))
+            // reaches 1/255 (forward.cu:590), i.e. where q(d) = -power <= log(255*o).  pmin =
+            // -(log(255*o) + slack) and the slopes -B/C, -B/A let a warp minimise the convex
+            // quadratic q over its pixel rectangle exactly (fdgs_common.cuh: rect_may_contribute).
+            // Conservative: used only to SKIP work, never to change a result.
+            float pmin, sbc = 0.f, sba = 0.f;
+            const float cdet = conx * conz - cony * cony;
+            if (opacity < 0.00392156886f) {   // alpha <= o < 1/255 everywhere: never contributes
+                pmin = INFINITY;
+            } else if (!(opacity <= 3.0e38f) || !(conx > 0.f) || !(conz > 0.f) || !(cdet > 0.f) || !(cdet <= 3.0e38f)) {
+                pmin = -INFINITY;             // irregular inputs (NaN/inf opacity, non-PD conic): no culling
+            } else {
+                pmin = -(logf(255.0f * opacity) + 0.02f);
+                sbc = -cony / conz;
+                sba = -cony / conx;
+                if (!(fabsf(sbc) <= 3.0e38f) || !(fabsf(sba) <= 3.0e38f)) { pmin = -INFINITY; sbc = sba = 0.f; }
+            }
+            const float fx = a.flows ? a.flows[2 * idx + 0] : 0.f, fy = a.flows ? a.flows[2 * idx + 1] : 0.f;
+            float4* dst = reinterpret_cast<float4*>(a.grec + idx);
+            dst[0] = make_float4(px, py, pmin, __uint_as_float((uint32_t)idx));
+            dst[1] = make_float4(conx, cony, conz, opacity);
+            dst[2] = make_float4(rgb[0], rgb[1], rgb[2], depth);
+            dst[3] = make_float4(fx, fy, sbc, sba);
         }
     }
 }

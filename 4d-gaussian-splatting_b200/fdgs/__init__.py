@@ -25,7 +25,7 @@ ABI_SYMBOLS = (
     "fdgs_profile_enable", "fdgs_profile_read", "fdgs_launch_count",
 )
 
-STAGE_NAMES = ("preprocess_fwd", "scan", "emit_keys", "sort", "pack_instances", "blend_fwd", "blend_bwd",
+STAGE_NAMES = ("preprocess_fwd", "bin_count_scan", "bin_scatter", "tile_sort_pack", "reserved", "blend_fwd", "blend_bwd",
                "preprocess_bwd")
 
 _lib = None

@@ -358,9 +358,9 @@ def main():
         dom = max(stage_ms, key=stage_ms.get)
         alg = {"blend_bwd": 52.0 * R + 36.0 * N + 52.0 * P_vis, "blend_fwd": 28.0 * R + 32.0 * N,
                "preprocess_bwd": 1376.0 * P_vis + 88.0 * wl.P, "preprocess_fwd": 84.0 * wl.P + 655.0 * P_vis,
-               "sort": 24.0 * R, "pack_instances": 44.0 * R, "emit_keys": 12.0 * R + 20.0 * wl.P}.get(dom, 0.0)
+               "tile_sort_pack": 80.0 * R, "bin_scatter": 8.0 * R + 4.0 * wl.P + 32.0 * P_vis}.get(dom, 0.0)
         ach = alg / (stage_ms[dom] * 1e-3) / 1e9
-        b_fwd = 84.0 * wl.P + 655.0 * P_vis + 72.0 * R + 32.0 * N
+        b_fwd = 84.0 * wl.P + 719.0 * P_vis + 88.0 * R + 32.0 * N
         b_bwd = 52.0 * R + 36.0 * N + 1428.0 * P_vis
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": None, "peak_source": peak_src,
