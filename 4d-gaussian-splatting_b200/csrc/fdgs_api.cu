@@ -305,8 +305,8 @@ int fdgs_backward(const fdgs_backward_args* a, void* stream_v) {
     if (W <= 0 || H <= 0 || R < 0) return fail(FDGS_ERR_INVALID_ARG, "bad width / height / R");
     if (!a->geom_buffer || !a->image_buffer || (R > 0 && !a->binning_buffer))
         return fail(FDGS_ERR_INVALID_ARG, "scratch buffers of the forward pass required");
-    if (!a->dL_dpix || !a->dL_depths || !a->dL_masks || !a->dL_dpix_flow)
-        return fail(FDGS_ERR_INVALID_ARG, "pixel gradients required");
+    // dL_depths / dL_masks / dL_dpix_flow may be NULL: no upstream gradient for that image
+    if (!a->dL_dpix) return fail(FDGS_ERR_INVALID_ARG, "colour image gradient required");
     if (!a->dL_dmean2D || !a->dL_dconic || !a->dL_dopacity || !a->dL_dcolor || !a->dL_dflows || !a->dL_dmean3D ||
         !a->dL_dcov3D || !a->dL_dts || !a->dL_dscale || !a->dL_dscale_t || !a->dL_drot || !a->dL_drot_r)
         return fail(FDGS_ERR_INVALID_ARG, "gradient outputs required");

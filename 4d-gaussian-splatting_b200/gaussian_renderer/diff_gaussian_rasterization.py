@@ -89,6 +89,10 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.save_for_backward(colors_precomp, means3D, out_means3D, scales, rotations, cov3Ds_precomp, radii, sh,
                               flow_2d, opacities, ts, scales_t, rotations_r, geom_buf, binning_buf, img_buf)
         ctx.mark_non_differentiable(radii)
+        # outputs the loss does not touch arrive as None in backward() instead of zero images; the
+        # library then skips their recurrences (the reference always blends all seven channels back)
+        ctx.set_materialize_grads(False)
+        ctx.image_shape = tuple(color.shape)
         # alpha = 1 - T (reference: :140)
         return color, radii, depth, 1 - T, flow, covs_com
 
@@ -97,6 +101,12 @@ class _RasterizeGaussians(torch.autograd.Function):
         s = ctx.raster_settings
         (colors_precomp, means3D, out_means3D, scales, rotations, cov3Ds_precomp, radii, sh, flow_2d, opacities,
          ts, scales_t, rotations_r, geom_buf, binning_buf, img_buf) = ctx.saved_tensors
+        if grad_out_color is None:
+            grad_out_color = torch.zeros(ctx.image_shape, dtype=torch.float32, device=means3D.device)
+        none = torch.empty(0, dtype=torch.float32, device=means3D.device)   # "no gradient" placeholder
+        grad_depth = none if grad_depth is None else grad_depth
+        grad_alpha = none if grad_alpha is None else grad_alpha
+        grad_flow = none if grad_flow is None else grad_flow
         # positional layout of _C.rasterize_gaussians_backward (reference: :154-190, rasterize_points.h:51-89)
         args = (s.bg, means3D, out_means3D, radii, colors_precomp, flow_2d, opacities, ts, scales, scales_t,
                 rotations, rotations_r, s.scale_modifier, cov3Ds_precomp, ctx.prefilter_var, s.viewmatrix,

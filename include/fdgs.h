@@ -140,9 +140,9 @@ typedef struct fdgs_backward_args {
     const char* binning_buffer;
     const char* image_buffer;
     const float* dL_dpix;         /* [3,H,W]                                   */
-    const float* dL_depths;       /* [1,H,W]                                   */
-    const float* dL_masks;        /* [1,H,W] grad of alpha = 1 - T             */
-    const float* dL_dpix_flow;    /* [2,H,W]                                   */
+    const float* dL_depths;       /* [1,H,W]  or NULL = no gradient (all zero) */
+    const float* dL_masks;        /* [1,H,W]  grad of alpha = 1 - T, or NULL   */
+    const float* dL_dpix_flow;    /* [2,H,W]  or NULL                          */
     int debug;
     /* Outputs.  The five "blend" gradients must be ZERO on entry (they are
      * accumulated into, like the reference: rasterize_points.cu:201-213); the
