@@ -25,12 +25,12 @@
 //                 starts at tile_offset + column prefix, so a shared-memory atomicAdd hands out the
 //                 final slot of the 64-bit key depth_bits<<32 | index.  Order inside a CTA's
 //                 segment is arbitrary; step 4 makes it canonical.
-//   4. sort+pack  tile_sort_pack_kernel: one CTA per tile sorts the tile's keys in shared memory
-//                 (bitonic network on 64-bit keys; a second, large-shared-memory instantiation takes
-//                 the tiles above 4096 instances, and tiles above ~25k run the same network in place in
-//                 global memory) and then writes, in sorted order, the
-//                 64-byte instance records the blend kernels stream with cp.async.bulk, plus the
-//                 sorted index list (the reference's point_list, kept for the parity tests).
+//   4. sort       tile_sort_kernel: one CTA per tile merge-sorts the tile's keys in shared memory (a
+//                 second, large-shared-memory instantiation takes the tiles above 2048 instances;
+//                 tiles above 16384 fall back to a bitonic network in place in global memory) and
+//                 writes the sorted index list (the reference's point_list).
+//   5. pack       pack_records_kernel: gathers the 64-byte per-Gaussian records into tile-sorted
+//                 order, the contiguous stream the blend kernels read with cp.async.bulk.
 //
 // Traffic per instance: 8 B key write + 8 B read + 64 B record write (+ 64 B L2-resident record
 // read), versus ~200 B for the reference's 8-pass radix sort.
@@ -176,13 +176,96 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int num_tiles, 
     if (tid == 0) { info[0] = carry; info[1] = max_count; }
 }
 
-// ---- 4. per-tile sort + pack --------------------------------------------------------------------------
-constexpr int SORT_SMALL_THREADS = 256, SORT_SMALL_KEYS = 4096;      // 32 KB of keys, ~6 CTAs per SM
-constexpr int SORT_LARGE_THREADS = 1024, SORT_LARGE_KEYS = 25600;    // 200 KB of keys, 1 CTA per SM
+// ---- 4. per-tile sort ------------------------------------------------------------------------------------
+// Block merge sort of one tile's 64-bit keys: every thread sorts KPT keys in registers (bitonic
+// network, static indices), then log2(runs) merge passes through shared memory -- each thread finds
+// its KPT-element slice of the merged pair of runs with a merge-path binary search and merges it
+// serially.  O(n log n) compare work and one shared-memory round trip per pass, against the
+// O(n log^2 n) exchanges of a bitonic network.  Shared-memory slots are padded by one key per KPT
+// (odd 8-byte stride per thread -> conflict-free stores).
+constexpr uint64_t KEY_SENTINEL = ~0ull;   // > every real key (depth bits of a positive float are < 0x7f800000)
+
+__device__ __forceinline__ void key_cswap(uint64_t& a, uint64_t& b) {
+    if (a > b) { const uint64_t t = a; a = b; b = t; }
+}
+
+template <int KPT>
+__device__ __forceinline__ void register_sort(uint64_t (&k)[KPT]) {
+    static_assert((KPT & (KPT - 1)) == 0, "power of two");
+#pragma unroll
+    for (int size = 2; size <= KPT; size <<= 1) {
+#pragma unroll
+        for (int i = 0; i < KPT; ++i) {
+            const int j = i ^ (size - 1);
+            if (j > i) key_cswap(k[i], k[j]);
+        }
+#pragma unroll
+        for (int stride = size >> 2; stride > 0; stride >>= 1) {
+#pragma unroll
+            for (int i = 0; i < KPT; ++i)
+                if ((i & stride) == 0) key_cswap(k[i], k[i + stride]);
+        }
+    }
+}
+
+template <int KPT>
+__device__ __forceinline__ int slot(int p) {   // padded shared-memory position of logical key p
+    return p + p / KPT;
+}
+
+// Sorts gk[0..n) (n <= THREADS * KPT) and writes the sorted Gaussian indices to ids[0..n).
+template <int THREADS, int KPT>
+__device__ __forceinline__ void block_merge_sort(uint64_t* sm, const uint64_t* __restrict__ gk, int n,
+                                                 uint32_t* __restrict__ ids) {
+    const int tid = threadIdx.x;
+    const int nthr = (n + KPT - 1) / KPT;   // threads that own at least one real key
+    const int N = nthr * KPT;
+    const int start = tid * KPT;
+    uint64_t k[KPT];
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) k[i] = (start + i < n) ? gk[start + i] : KEY_SENTINEL;
+    if (tid < nthr) register_sort<KPT>(k);
+    for (int len = KPT; len < N; len <<= 1) {
+        __syncthreads();   // the previous pass has finished reading
+        if (tid < nthr) {
+#pragma unroll
+            for (int i = 0; i < KPT; ++i) sm[slot<KPT>(start + i)] = k[i];
+        }
+        __syncthreads();
+        if (tid < nthr) {
+            const int pair = start & ~(2 * len - 1);
+            const int a0 = pair, a1 = min(pair + len, N), b0 = a1, b1 = min(pair + 2 * len, N);
+            const int diag = start - pair;
+            // merge path: how many of the first `diag` outputs come from run A
+            int lo = max(0, diag - (b1 - b0)), hi = min(diag, a1 - a0);
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const uint64_t ka = sm[slot<KPT>(a0 + mid)], kb = sm[slot<KPT>(b0 + diag - 1 - mid)];
+                if (ka <= kb) lo = mid + 1;
+                else hi = mid;
+            }
+            int ia = a0 + lo, ib = b0 + diag - lo;
+            uint64_t ka = (ia < a1) ? sm[slot<KPT>(ia)] : KEY_SENTINEL;
+            uint64_t kb = (ib < b1) ? sm[slot<KPT>(ib)] : KEY_SENTINEL;
+#pragma unroll
+            for (int i = 0; i < KPT; ++i) {
+                const bool take_a = ka <= kb;
+                k[i] = take_a ? ka : kb;
+                if (take_a) { ++ia; ka = (ia < a1) ? sm[slot<KPT>(ia)] : KEY_SENTINEL; }
+                else { ++ib; kb = (ib < b1) ? sm[slot<KPT>(ib)] : KEY_SENTINEL; }
+            }
+        }
+    }
+    if (tid < nthr) {
+#pragma unroll
+        for (int i = 0; i < KPT; ++i)
+            if (start + i < n) ids[start + i] = (uint32_t)(k[i] & 0xffffffffu);
+    }
+}
 
 // Bitonic sorting network in its "flip" form (every sub-sequence ascending), for an arbitrary n:
 // positions >= n behave as +infinity and never move, so comparisons that would touch them are
-// simply skipped -- no padding storage, which lets oversize tiles sort in place in global memory.
+// simply skipped.  Only used in place in global memory, for tiles too large for shared memory.
 __device__ __forceinline__ void bitonic_sort(uint64_t* k, int n, int tid, int nthreads) {
     int np = 1;
     while (np < n) np <<= 1;
@@ -213,52 +296,45 @@ __device__ __forceinline__ void bitonic_sort(uint64_t* k, int n, int tid, int nt
     __syncthreads();
 }
 
-// Handles the tiles with n_lo < n <= n_hi; keys of tiles above CAP are sorted in place in global memory.
-template <int THREADS, int CAP>
-__global__ void __launch_bounds__(THREADS) tile_sort_pack_kernel(int n_lo, int n_hi, const uint2* __restrict__ ranges,
-                                                                 uint64_t* __restrict__ keys,
-                                                                 const InstRec* __restrict__ grec,
-                                                                 InstRec* __restrict__ recs,
-                                                                 uint32_t* __restrict__ point_list) {
+constexpr int SORT_SMALL_THREADS = 256, SORT_SMALL_KEYS = 2048;      // 18 KB of shared memory, 8 keys per thread
+constexpr int SORT_LARGE_THREADS = 1024, SORT_LARGE_KEYS = 16384;    // 139 KB of shared memory, 16 keys per thread
+
+// One CTA per tile.  LARGE = false handles the tiles with n <= 2048, LARGE = true those above (launched
+// only if the largest tile needs it); tiles above 16384 instances sort in place in global memory.
+template <bool LARGE>
+__global__ void __launch_bounds__(LARGE ? SORT_LARGE_THREADS : SORT_SMALL_THREADS)
+tile_sort_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ keys, uint32_t* __restrict__ point_list) {
     extern __shared__ uint64_t skeys[];
     const uint2 range = ranges[blockIdx.x];
     const int n = (int)(range.y - range.x);
-    if (n <= n_lo || n > n_hi) return;
-    const int tid = threadIdx.x;
+    if (n <= 0) return;
     uint64_t* gk = keys + range.x;
-    const uint64_t* sorted;
-    if (n <= CAP) {
-        for (int i = tid; i < n; i += THREADS) skeys[i] = gk[i];
-        bitonic_sort(skeys, n, tid, THREADS);
-        sorted = skeys;
+    uint32_t* ids = point_list + range.x;
+    if (!LARGE) {
+        if (n > SORT_SMALL_KEYS) return;
+        block_merge_sort<SORT_SMALL_THREADS, 8>(skeys, gk, n, ids);
     } else {
-        bitonic_sort(gk, n, tid, THREADS);
-        sorted = gk;
-    }
-    // pack: one 64-byte record per instance, in sorted order; 4 lanes copy one record (16 B each),
-    // four records in flight per lane
-    const int part = tid & 3;
-    constexpr int RPI = THREADS / 4;   // records per iteration step
-    for (int i0 = tid >> 2; i0 < n; i0 += 4 * RPI) {
-        float4 v[4];
-        uint32_t id[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * RPI;
-            if (i < n) {
-                id[u] = (uint32_t)(sorted[i] & 0xffffffffu);
-                v[u] = reinterpret_cast<const float4*>(grec + id[u])[part];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * RPI;
-            if (i < n) {
-                reinterpret_cast<float4*>(recs + range.x + i)[part] = v[u];
-                if (part == 0) point_list[range.x + i] = id[u];
-            }
+        if (n <= SORT_SMALL_KEYS) return;
+        if (n <= SORT_LARGE_KEYS) {
+            block_merge_sort<SORT_LARGE_THREADS, 16>(skeys, gk, n, ids);
+        } else {
+            bitonic_sort(gk, n, threadIdx.x, SORT_LARGE_THREADS);
+            for (int i = threadIdx.x; i < n; i += SORT_LARGE_THREADS) ids[i] = (uint32_t)(gk[i] & 0xffffffffu);
         }
     }
+}
+
+// ---- 5. pack ----------------------------------------------------------------------------------------------
+// recs[i] = grec[point_list[i]]: the 64-byte records in tile-sorted order, so the blend kernels can
+// stream a tile's work list with one cp.async.bulk per 128 instances.  4 lanes copy one record.
+__global__ void __launch_bounds__(256) pack_records_kernel(int R, const uint32_t* __restrict__ point_list,
+                                                           const InstRec* __restrict__ grec, InstRec* __restrict__ recs) {
+    const size_t q = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const size_t i = q >> 2;
+    if (i >= (size_t)R) return;
+    const int part = (int)(q & 3);
+    const uint32_t id = point_list[i];
+    reinterpret_cast<float4*>(recs + i)[part] = reinterpret_cast<const float4*>(grec + id)[part];
 }
 
 // test hook: unpack the per-Gaussian records into the reference's plain arrays; `radii` is any
@@ -325,27 +401,26 @@ cudaError_t launch_bin_scatter(int P, const InstRec* grec, const int* radii, int
     return launch_bin_pass<true>(P, grec, radii, grid_x, grid_y, matrix, tile_offset, keys, stream);
 }
 
-int tile_sort_pack_kernel_count(int max_count) { return max_count > SORT_SMALL_KEYS ? 2 : 1; }
+int tile_sort_pack_kernel_count(int max_count) { return max_count > SORT_SMALL_KEYS ? 3 : 2; }
 
-cudaError_t launch_tile_sort_pack(int num_tiles, int max_count, const uint2* ranges, uint64_t* keys, const InstRec* grec,
-                                  InstRec* recs, uint32_t* point_list, cudaStream_t stream) {
-    if (num_tiles <= 0) return cudaSuccess;
-    tile_sort_pack_kernel<SORT_SMALL_THREADS, SORT_SMALL_KEYS>
-        <<<num_tiles, SORT_SMALL_THREADS, SORT_SMALL_KEYS * sizeof(uint64_t), stream>>>(0, SORT_SMALL_KEYS, ranges, keys, grec,
-                                                                                        recs, point_list);
+cudaError_t launch_tile_sort_pack(int num_tiles, int max_count, int R, const uint2* ranges, uint64_t* keys,
+                                  const InstRec* grec, InstRec* recs, uint32_t* point_list, cudaStream_t stream) {
+    if (num_tiles <= 0 || R <= 0) return cudaSuccess;
+    constexpr size_t small_smem = (size_t)(SORT_SMALL_KEYS + SORT_SMALL_KEYS / 8) * sizeof(uint64_t);
+    constexpr size_t large_smem = (size_t)(SORT_LARGE_KEYS + SORT_LARGE_KEYS / 16) * sizeof(uint64_t);
+    tile_sort_kernel<false><<<num_tiles, SORT_SMALL_THREADS, small_smem, stream>>>(ranges, keys, point_list);
     if (max_count > SORT_SMALL_KEYS) {
         static bool attr_set = false;
         if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(tile_sort_pack_kernel<SORT_LARGE_THREADS, SORT_LARGE_KEYS>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)(SORT_LARGE_KEYS * sizeof(uint64_t)));
+            cudaError_t e = cudaFuncSetAttribute(tile_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)large_smem);
             if (e != cudaSuccess) return e;
             attr_set = true;
         }
-        tile_sort_pack_kernel<SORT_LARGE_THREADS, SORT_LARGE_KEYS>
-            <<<num_tiles, SORT_LARGE_THREADS, SORT_LARGE_KEYS * sizeof(uint64_t), stream>>>(
-                SORT_SMALL_KEYS, 0x7fffffff, ranges, keys, grec, recs, point_list);
+        tile_sort_kernel<true><<<num_tiles, SORT_LARGE_THREADS, large_smem, stream>>>(ranges, keys, point_list);
     }
+    const size_t quads = (size_t)R * 4;
+    pack_records_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, stream>>>(R, point_list, grec, recs);
     return cudaGetLastError();
 }
 

@@ -77,10 +77,20 @@ __global__ void __launch_bounds__(BF_THREADS) blend_fwd_kernel(const BlendFwdPar
 
     int b = 0;
     for (; b < nb; ++b) {
-        if (*done_warps == BF_WARPS) break;
         const int s = b % BF_STAGES;
         const uint32_t ph = (uint32_t)(b / BF_STAGES) & 1u;
-        mbar_wait(&sm.full[s], ph);
+        // Wait for batch b -- or for the whole tile to finish.  Once every warp is done the producer
+        // stops refilling (below), so a warp that ran ahead must not wait for a batch that will never
+        // come; lane 0 polls both conditions and the warp leaves together.
+        bool stop = false;
+        if (lane == 0) {
+            while (!mbar_try_wait(&sm.full[s], ph)) {
+                if (*done_warps == BF_WARPS) { stop = true; break; }
+            }
+            if (!stop && *done_warps == BF_WARPS) stop = true;
+        }
+        if (__any_sync(0xffffffffu, stop)) break;
+        mbar_wait(&sm.full[s], ph);   // already complete: gives every lane the acquire on the batch
         if (!warp_done) {
             const int cnt = min(BF_BATCH, n - b * BF_BATCH);
             const InstRec* st = sm.recs[s];

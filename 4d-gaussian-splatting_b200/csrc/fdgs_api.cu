@@ -6,6 +6,7 @@
 // ImageState / BinningState chunk carving (rasterizer_impl.cu:156-195, rasterizer_impl.h:21-73).
 #include <string.h>
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -37,6 +38,8 @@ std::mutex g_prof_mu;
 bool g_prof_on = false;
 std::vector<ProfEvent> g_prof_events;
 std::atomic<long long> g_kernel_launches{0};
+// FDGS_TRACE=1 + debug=true: print every stage to stderr before and after its synchronisation
+const bool g_trace = getenv("FDGS_TRACE") != nullptr;
 
 struct StageTimer {
     cudaEvent_t a = nullptr, b = nullptr;
@@ -66,7 +69,9 @@ struct StageTimer {
         FDGS_CUDA(expr, what);                                                                        \
         _t.stop(nk);                                                                                  \
         if (debug) {                                                                                  \
+            if (g_trace) fprintf(stderr, "[fdgs] %s launched, synchronising\n", what);               \
             cudaError_t _s = cudaStreamSynchronize(stream);                                           \
+            if (g_trace) fprintf(stderr, "[fdgs] %s done: %s\n", what, cudaGetErrorString(_s));      \
             if (_s != cudaSuccess)                                                                    \
                 return fail(FDGS_ERR_CUDA, std::string(what) + " (debug sync): " + cudaGetErrorString(_s)); \
         }                                                                                             \
@@ -281,7 +286,7 @@ int fdgs_forward(const fdgs_forward_args* a, fdgs_alloc_fn geom_alloc, void* geo
                                                   bin.keys, stream),
                    "bin_scatter");
         FDGS_STAGE(3, fdgs::tile_sort_pack_kernel_count(bin_info[1]),
-                   fdgs::launch_tile_sort_pack((int)img.tiles, bin_info[1], img.ranges, bin.keys, geom.grec, bin.recs,
+                   fdgs::launch_tile_sort_pack((int)img.tiles, bin_info[1], num_rendered, img.ranges, bin.keys, geom.grec, bin.recs,
                                                bin.point_list, stream),
                    "tile_sort_pack");
     }

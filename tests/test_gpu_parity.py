@@ -127,6 +127,41 @@ def test_colour_only_backward_equals_zero_aux_gradients(C, name):
             assert helpers.l2_rel(helpers.to_np(a), helpers.to_np(b)) < max(2e-5, 8 * noise), (gname, noise)
 
 
+@pytest.mark.parametrize("P,expect_min", [(4000, 0), (30000, 2049), (200000, 16385)])
+def test_tile_lists_sorted_and_complete(C, P, expect_min):
+    """Every path of the per-tile sort (<= 2048 keys: 8 keys per thread; <= 16384: the large
+    shared-memory instantiation; above: in place in global memory) must produce, for every tile,
+    exactly the instances whose tile rectangle covers it, ordered by (depth bits, Gaussian index) --
+    the order the reference's stable radix sort of tile|depth keys gives (rasterizer_impl.cu:325)."""
+    cfg = dict(P=P, W=32, H=32, seed=4242 + P)
+    o = run_cuda(C, cfg, with_backward=False)
+    radii = helpers.to_np(o["fw"][5]).astype(np.int64)
+    px = helpers.to_np(o["means2D"])[:, 0].astype(np.float32)
+    py = helpers.to_np(o["means2D"])[:, 1].astype(np.float32)
+    depth_bits = helpers.to_np(o["depths"]).astype(np.float32).view(np.uint32).astype(np.uint64)
+    ranges = helpers.to_np(o["ranges"]).reshape(-1, 2).astype(np.int64)
+    plist = helpers.to_np(o["point_list"]).astype(np.int64)
+    gx = gy = 2
+    r = radii.astype(np.float32)
+    f = np.float32
+    x0 = np.clip(((px - r) * f(0.0625)).astype(np.int64), 0, gx)
+    y0 = np.clip(((py - r) * f(0.0625)).astype(np.int64), 0, gy)
+    x1 = np.clip(((((px + r) + f(16.0)) + f(-1.0)) * f(0.0625)).astype(np.int64), 0, gx)
+    y1 = np.clip(((((py + r) + f(16.0)) + f(-1.0)) * f(0.0625)).astype(np.int64), 0, gy)
+    vis = radii > 0
+    assert (ranges[:, 1] - ranges[:, 0]).max() >= expect_min, "configuration does not reach the intended sort path"
+    assert (ranges[:, 1] - ranges[:, 0]).sum() == int(o["fw"][0]) == len(plist)
+    for ty in range(gy):
+        for tx in range(gx):
+            lo, hi = ranges[ty * gx + tx]
+            ids = plist[lo:hi]
+            want = np.nonzero(vis & (x0 <= tx) & (tx < x1) & (y0 <= ty) & (ty < y1))[0]
+            key = (depth_bits[want] << np.uint64(32)) | want.astype(np.uint64)
+            want = want[np.argsort(key, kind="stable")]
+            assert len(ids) == len(want)
+            assert (ids == want).all()
+
+
 # ---------------------------------------------------------------------------------------------------
 # 2. the compiled reference at BASELINE sizes
 # ---------------------------------------------------------------------------------------------------

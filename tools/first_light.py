@@ -82,6 +82,10 @@ def run_config(name, cfg, golden_dir=None):
     grads = helpers.pixel_grads(cfg, device=dev)
     mine_b = C.rasterize_gaussians_backward(*helpers.bwd_args(st, sc, cfg, mine, grads))
     torch.cuda.synchronize()
+    # colour-only backward (the training-loss case), so that profiles of a --no-timing run cover it
+    e_ = torch.empty(0, device=dev)
+    C.rasterize_gaussians_backward(*helpers.bwd_args(st, sc, cfg, mine, (grads[0], e_, e_, e_)))
+    torch.cuda.synchronize()
     mg = C.debug_export_geom(mine[6], P)
     mb = C.debug_export_binning(mine[7], mine[8], mine[0], W, H)
     ncm = mb[2]
