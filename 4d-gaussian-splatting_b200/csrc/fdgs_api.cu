@@ -320,6 +320,7 @@ int fdgs_backward(const fdgs_backward_args* a, void* stream_v) {
     ImageState img = ImageState::carve(align128(const_cast<char*>(a->image_buffer)), W, H);
     BinningState bin = BinningState::carve(a->binning_buffer ? align128(const_cast<char*>(a->binning_buffer)) : nullptr, R);
 
+    bool blend_raw = false;
     if (R > 0) {
         fdgs::BlendBwdParams bp;
         bp.W = W; bp.H = H; bp.grid_x = grid_x; bp.grid_y = grid_y;
@@ -328,6 +329,7 @@ int fdgs_backward(const fdgs_backward_args* a, void* stream_v) {
         bp.dL_dpix = a->dL_dpix; bp.dL_depths = a->dL_depths; bp.dL_masks = a->dL_masks; bp.dL_dpix_flow = a->dL_dpix_flow;
         bp.dL_dmean2D = a->dL_dmean2D; bp.dL_dconic = a->dL_dconic; bp.dL_dopacity = a->dL_dopacity;
         bp.dL_dcolor = a->dL_dcolor; bp.dL_dflows = a->dL_dflows;
+        blend_raw = fdgs::blend_bwd_is_raw(bp);
         FDGS_STAGE(6, 1, fdgs::launch_blend_bwd(bp, stream), "blend_bwd");
     }
     fdgs::PreprocessBwdParams pb;
@@ -345,6 +347,7 @@ int fdgs_backward(const fdgs_backward_args* a, void* stream_v) {
     pb.timestamp = a->timestamp; pb.time_duration = a->time_duration;
     pb.rot_4d = a->rot_4d; pb.gaussian_dim = a->gaussian_dim; pb.force_sh_3d = a->force_sh_3d;
     pb.has_scales = (a->scales != nullptr) ? 1 : 0;
+    pb.grec = geom.grec; pb.blend_raw = blend_raw ? 1 : 0; pb.W = W; pb.H = H;
     sh_staging(a->shs, a->M, &pb.sh_bulk_ok, &pb.sh_row_stride_floats);
     if (a->dL_dsh && (reinterpret_cast<uintptr_t>(a->dL_dsh) % 16) != 0) pb.sh_bulk_ok = 0;
     pb.dL_dmean2D = a->dL_dmean2D; pb.dL_dconic = a->dL_dconic; pb.dL_dopacity = a->dL_dopacity; pb.dL_dcolor = a->dL_dcolor;

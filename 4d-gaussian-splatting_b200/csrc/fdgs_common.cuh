@@ -303,6 +303,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// same, but a warp that has to wait gives its issue slots to the warps that are still working
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+}
 // global -> shared bulk copy (SASS: UBLKCP), completion signalled on `bar` (complete_tx::bytes).
 // dst, src and bytes must be multiples of 16.
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {

@@ -94,6 +94,10 @@ struct BlendBwdParams {
     float* dL_dflows;     // [P,2]
 };
 cudaError_t launch_blend_bwd(const BlendBwdParams& p, cudaStream_t stream);
+// true when launch_blend_bwd(p) leaves RAW moment sums (W10, W01 | W20, W11, W02 | W00 of w = G dL/dalpha
+// about each Gaussian's mean) in dL_dmean2D.xy / dL_dconic / dL_dopacity instead of the final
+// gradients; launch_preprocess_bwd finishes them (PreprocessBwdParams::blend_raw)
+bool blend_bwd_is_raw(const BlendBwdParams& p);
 
 // ---- backward preprocess ------------------------------------------------------------------------
 struct PreprocessBwdParams {
@@ -121,10 +125,13 @@ struct PreprocessBwdParams {
     int has_scales;         // scales != NULL in the reference's sense (backward.cu:908)
     int sh_bulk_ok;         // SH rows are 16-byte aligned and 16-byte multiples: stream with cp.async.bulk
     int sh_row_stride_floats;
-    const float* dL_dmean2D;
-    const float* dL_dconic;
+    float* dL_dmean2D;      // in/out when blend_raw
+    float* dL_dconic;       // in/out when blend_raw
     float* dL_dopacity;     // in/out
     const float* dL_dcolor;
+    const InstRec* grec;    // per-Gaussian records of the forward (conic, blended opacity)
+    int blend_raw;          // dL_dmean2D.xy / dL_dconic hold raw moment sums (blend_bwd v2)
+    int W, H;
     float* dL_dmean3D;
     float* dL_dcov3D;
     float* dL_dsh;

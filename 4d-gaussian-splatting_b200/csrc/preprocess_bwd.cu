@@ -335,9 +335,28 @@ __global__ void __launch_bounds__(GB_THREADS) geom_bwd_kernel(const PreprocessBw
 #pragma unroll
         for (int i = 0; i < 6; ++i) c3[i] = a.cov3D[6 * idx + i];
 
+        // blend_bwd v2 leaves moment sums of w = G dL/dalpha about the mean: W10, W01 in dL_dmean2D.xy,
+        // W20, W11, W02 in dL_dconic.  Their per-Gaussian linear map to the reference's gradients
+        // (backward.cu:1119-1134: dG/ddel = -G (A dx + B dy), ddelx/dx = W/2, dL/dconic = -0.5 G d d^T dL/dG,
+        // dL/dG = opacity dL/dalpha) is applied here, once, instead of per (pixel, Gaussian) pair.
+        float d2x = a.dL_dmean2D[3 * idx + 0], d2y = a.dL_dmean2D[3 * idx + 1];
+        float dcx = a.dL_dconic[4 * idx + 0], dcy = a.dL_dconic[4 * idx + 1], dcz = a.dL_dconic[4 * idx + 3];
+        if (a.blend_raw) {
+            const float4 con = a.grec[idx].q1;   // A, B, C, blended opacity
+            const float W10 = d2x, W01 = d2y;
+            d2x = -0.5f * (float)a.W * con.w * (con.x * W10 + con.y * W01);
+            d2y = -0.5f * (float)a.H * con.w * (con.z * W01 + con.y * W10);
+            const float hs = -0.5f * con.w;
+            dcx *= hs; dcy *= hs; dcz *= hs;
+            a.dL_dmean2D[3 * idx + 0] = d2x;
+            a.dL_dmean2D[3 * idx + 1] = d2y;
+            a.dL_dconic[4 * idx + 0] = dcx;
+            a.dL_dconic[4 * idx + 1] = dcy;
+            a.dL_dconic[4 * idx + 3] = dcz;
+        }
+
         // ---------------- computeCov2DCUDA, backward.cu:486-617 ----------------
         {
-            const float dcx = a.dL_dconic[4 * idx + 0], dcy = a.dL_dconic[4 * idx + 1], dcz = a.dL_dconic[4 * idx + 3];
             Proj2D Pj;
             build_T(V, mx, my, mz, a.focal_x, a.focal_y, a.tan_fovx, a.tan_fovy, Pj);
             const float limx = fmul(1.3f, a.tan_fovx), limy = fmul(1.3f, a.tan_fovy);
@@ -399,7 +418,6 @@ __global__ void __launch_bounds__(GB_THREADS) geom_bwd_kernel(const PreprocessBw
             const float m_w = 1.0f / (m_hw + 0.0000001f);
             const float mul1 = (Pm[0] * mx + Pm[4] * my + Pm[8] * mz + Pm[12]) * m_w * m_w;
             const float mul2 = (Pm[1] * mx + Pm[5] * my + Pm[9] * mz + Pm[13]) * m_w * m_w;
-            const float d2x = a.dL_dmean2D[3 * idx + 0], d2y = a.dL_dmean2D[3 * idx + 1];
             g_mean[0] += (Pm[0] * m_w - Pm[3] * mul1) * d2x + (Pm[1] * m_w - Pm[3] * mul2) * d2y;
             g_mean[1] += (Pm[4] * m_w - Pm[7] * mul1) * d2x + (Pm[5] * m_w - Pm[7] * mul2) * d2y;
             g_mean[2] += (Pm[8] * m_w - Pm[11] * mul1) * d2x + (Pm[9] * m_w - Pm[11] * mul2) * d2y;

@@ -200,6 +200,42 @@ def test_full_size_vs_compiled_reference(C, name):
         assert err < max(1e-4, 8 * noise), (gname, err, noise)
 
 
+@pytest.mark.parametrize("name", ["small", "ragged", "negfov", "mid", "cfg2", "cfg3"])
+def test_colour_only_backward_vs_compiled_reference(C, name):
+    """The training default: only the colour image carries a gradient.  That selects the tensor-core
+    blend-backward (polynomial power + mma reduction, blend_bwd.cu v2); the reference gets explicit
+    zero images for depth / alpha / flow.  Same bar as the general path: 1e-4 in the L2 sense or a few
+    times the reference's own run-to-run atomic noise."""
+    if not oracle_py.ref_available():
+        pytest.skip("oracle/_ref/ref_rasterizer.so not present")
+    ref = oracle_py.ref_module()
+    cfg, cam, sc, st = helpers.build(name, device=DEV)
+    gc, gd, ga, gf = helpers.pixel_grads(cfg, device=DEV)
+    e = torch.empty(0, device=DEV)
+    fw = C.rasterize_gaussians(*helpers.fwd_args(st, sc, cfg))
+    ours = C.rasterize_gaussians_backward(*helpers.bwd_args(st, sc, cfg, fw, (gc, e, e, e)))
+    rf = ref.rasterize_gaussians(*helpers.fwd_args(st, sc, cfg))
+    zeros = (gc, 0 * gd, 0 * ga, 0 * gf)
+    rb = ref.rasterize_gaussians_backward(*helpers.bwd_args(st, sc, cfg, rf, zeros))
+    rb2 = ref.rasterize_gaussians_backward(*helpers.bwd_args(st, sc, cfg, rf, zeros))
+    torch.cuda.synchronize()
+    for gname, a, b, b2 in zip(helpers.GRAD_NAMES, ours, rb, rb2):
+        if b.numel() == 0:
+            continue
+        assert torch.isfinite(a).all(), gname
+        nb = b.double().norm().item()
+        if nb == 0.0:
+            assert float(a.abs().max()) == 0.0, gname
+            continue
+        scale = b.abs().max().item()
+        err = (a - b).abs().max().item() / scale
+        noise = (b2 - b).abs().max().item() / scale
+        l2 = ((a - b).double().norm() / nb).item()
+        l2n = ((b2 - b).double().norm() / nb).item()
+        assert l2 < 1e-4 or l2 < 5 * l2n, (gname, l2, l2n)
+        assert err < max(1e-4, 8 * noise), (gname, err, noise)
+
+
 # ---------------------------------------------------------------------------------------------------
 # 3. the CPU oracle, including branches without golden coverage
 # ---------------------------------------------------------------------------------------------------
