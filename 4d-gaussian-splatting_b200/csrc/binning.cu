@@ -11,7 +11,8 @@
 // That freedom is what this file exploits; no global sort exists here:
 //
 //   1. count      bin_pass_kernel<false>: BIN_CTAS persistent CTAs, each owning one contiguous chunk of
-//                 Gaussians, histogram the tiles their rendered Gaussians touch in SHARED memory
+//                 Gaussians (read as compact 16-byte bin records: tile rectangle + depth bits, written by
+//                 the preprocess), histogram the tiles their rendered Gaussians touch in SHARED memory
 //                 (a warp walks one Gaussian's tile rectangle with 32 lanes) and store the
 //                 histogram as one row of a [BIN_CTAS][tiles] matrix.  No global atomics.
 //   2. offsets    column_scan_kernel: one thread per tile, exclusive prefix down the matrix column
@@ -25,12 +26,13 @@
 //                 starts at tile_offset + column prefix, so a shared-memory atomicAdd hands out the
 //                 final slot of the 64-bit key depth_bits<<32 | index.  Order inside a CTA's
 //                 segment is arbitrary; step 4 makes it canonical.
-//   4. sort       tile_sort_kernel: one CTA per tile merge-sorts the tile's keys in shared memory (a
+//   4. sort+pack  tile_sort_kernel: one CTA per tile merge-sorts the tile's keys in shared memory (a
 //                 second, large-shared-memory instantiation takes the tiles above 2048 instances;
-//                 tiles above 16384 fall back to a bitonic network in place in global memory) and
-//                 writes the sorted index list (the reference's point_list).
-//   5. pack       pack_records_kernel: gathers the 64-byte per-Gaussian records into tile-sorted
-//                 order, the contiguous stream the blend kernels read with cp.async.bulk.
+//                 tiles above 16384 fall back to a bitonic network in place in global memory), writes
+//                 the sorted index list (the reference's point_list) and, from the ids still in shared
+//                 memory, gathers the 64-byte per-Gaussian records into tile-sorted order -- the
+//                 contiguous stream the blend kernels read with cp.async.bulk.  Gather latency of one
+//                 CTA overlaps the shared-memory sort of its SM neighbours.
 //
 // Traffic per instance: 8 B key write + 8 B read + 64 B record write (+ 64 B L2-resident record
 // read), versus ~200 B for the reference's 8-pass radix sort.
@@ -50,8 +52,7 @@ constexpr size_t BIN_SMEM_LIMIT = 200 * 1024;
 //                  tile_offset[t] + row[t] + (arrival order inside the CTA).
 // SMEM: histogram lives in shared memory; otherwise (very large tile grids) the CTA-private global row is used in place.
 template <bool SCATTER, bool SMEM>
-__global__ void __launch_bounds__(BIN_THREADS) bin_pass_kernel(int P, int chunk, const InstRec* __restrict__ grec,
-                                                               const int* __restrict__ radii, int grid_x, int grid_y,
+__global__ void __launch_bounds__(BIN_THREADS) bin_pass_kernel(int P, int chunk, const uint4* __restrict__ binrec, int grid_x,
                                                                int num_tiles, uint32_t* __restrict__ matrix,
                                                                const uint32_t* __restrict__ tile_offset,
                                                                uint64_t* __restrict__ keys) {
@@ -66,21 +67,18 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_pass_kernel(int P, int chunk,
     __syncthreads();
     const int begin = blockIdx.x * chunk;
     const int end = min(P, begin + chunk);
-    for (int g0 = begin + warp * 32; g0 < end; g0 += BIN_THREADS) {
-        const int idx = g0 + lane;
-        int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-        uint32_t dbits = 0;
-        bool vis = false;
-        if (idx < end) {
-            const int radius = radii[idx];
-            if (radius > 0) {
-                const float4 q0 = grec[idx].q0;   // x, y, pmin, id
-                get_rect(q0.x, q0.y, radius, grid_x, grid_y, x0, y0, x1, y1);
-                // key: depth bits (positive floats: integer order == float order) then Gaussian index
-                if (SCATTER) dbits = __float_as_uint(grec[idx].q2.w);
-                vis = true;
-            }
-        }
+    // one coalesced 16-byte record per Gaussian (written by the preprocess for EVERY Gaussian; an empty
+    // rectangle = not rendered); the next iteration's record is in flight while this one is binned
+    const uint4 none = make_uint4(0u, 0u, 0u, 0u);
+    int g0 = begin + warp * 32;
+    uint4 nxt = (g0 + lane < end) ? binrec[g0 + lane] : none;
+    for (; g0 < end; g0 += BIN_THREADS) {
+        const uint4 br = nxt;
+        const int gn = g0 + BIN_THREADS + lane;
+        nxt = (gn < end) ? binrec[gn] : none;
+        // x = x0 | y0 << 16, y = x1 | y1 << 16 (tile coordinates), z = depth bits
+        const int x0 = (int)(br.x & 0xffffu), y0 = (int)(br.x >> 16), x1 = (int)(br.y & 0xffffu), y1 = (int)(br.y >> 16);
+        const bool vis = (x1 > x0) && (y1 > y0);
         uint32_t mask = __ballot_sync(0xffffffffu, vis);
         while (mask) {
             const int src = __ffs(mask) - 1;
@@ -89,7 +87,8 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_pass_kernel(int P, int chunk,
             const int bx1 = __shfl_sync(0xffffffffu, x1, src), by1 = __shfl_sync(0xffffffffu, y1, src);
             const int w = bx1 - bx0, n = w * (by1 - by0);
             uint64_t key = 0;
-            if (SCATTER) key = ((uint64_t)__shfl_sync(0xffffffffu, dbits, src) << 32) | (uint32_t)(g0 + src);
+            // key: depth bits (positive floats: integer order == float order) then Gaussian index
+            if (SCATTER) key = ((uint64_t)__shfl_sync(0xffffffffu, br.z, src) << 32) | (uint32_t)(g0 + src);
             for (int i = lane; i < n; i += 32) {
                 const int ry = i / w, rx = i - ry * w;
                 const int t = (by0 + ry) * grid_x + bx0 + rx;
@@ -105,28 +104,42 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_pass_kernel(int P, int chunk,
 }
 
 // ---- 2. offsets ------------------------------------------------------------------------------------
+// 32 tiles x 8 row groups per CTA: every thread owns <= ceil(rows / 8) consecutive rows of one tile column
+// (kept in registers), the groups' partial sums are combined through shared memory.  Coalesced along tiles.
+constexpr int CS_GROUPS = 8;
+constexpr int CS_MAXROWS = (BIN_CTAS + CS_GROUPS - 1) / CS_GROUPS;
 __global__ void __launch_bounds__(256) column_scan_kernel(int num_tiles, int rows, uint32_t* __restrict__ matrix,
                                                           uint32_t* __restrict__ tile_total) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint32_t part[CS_GROUPS][32];
+    const int tx = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int t = blockIdx.x * 32 + tx;
+    const int per = (rows + CS_GROUPS - 1) / CS_GROUPS;
+    const int r0 = grp * per, r1 = min(rows, r0 + per);
+    uint32_t v[CS_MAXROWS];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < CS_MAXROWS; ++i) {
+        const int r = r0 + i;
+        v[i] = (t < num_tiles && r < r1) ? matrix[(size_t)r * num_tiles + t] : 0u;
+        sum += v[i];
+    }
+    part[grp][tx] = sum;
+    __syncthreads();
+    uint32_t run = 0, total = 0;
+#pragma unroll
+    for (int g = 0; g < CS_GROUPS; ++g) {
+        const uint32_t pg = part[g][tx];
+        if (g < grp) run += pg;
+        total += pg;
+    }
     if (t >= num_tiles) return;
-    uint32_t run = 0;
-    int c = 0;
-    for (; c + 4 <= rows; c += 4) {
-        uint32_t v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = matrix[(size_t)(c + u) * num_tiles + t];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            matrix[(size_t)(c + u) * num_tiles + t] = run;
-            run += v[u];
-        }
+    for (int i = 0; i < CS_MAXROWS; ++i) {
+        const int r = r0 + i;
+        if (r < r1) matrix[(size_t)r * num_tiles + t] = run;
+        run += v[i];
     }
-    for (; c < rows; ++c) {
-        const uint32_t v = matrix[(size_t)c * num_tiles + t];
-        matrix[(size_t)c * num_tiles + t] = run;
-        run += v;
-    }
-    tile_total[t] = run;
+    if (grp == 0) tile_total[t] = total;
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int num_tiles, const uint32_t* __restrict__ tile_total,
@@ -256,10 +269,41 @@ __device__ __forceinline__ void block_merge_sort(uint64_t* sm, const uint64_t* _
             }
         }
     }
+    __syncthreads();   // the last merge pass has finished reading the key array: reuse it for the sorted ids
+    uint32_t* sid = reinterpret_cast<uint32_t*>(sm);
     if (tid < nthr) {
 #pragma unroll
         for (int i = 0; i < KPT; ++i)
-            if (start + i < n) ids[start + i] = (uint32_t)(k[i] & 0xffffffffu);
+            if (start + i < n) {
+                const uint32_t id = (uint32_t)(k[i] & 0xffffffffu);
+                ids[start + i] = id;
+                sid[start + i] = id;
+            }
+    }
+    __syncthreads();
+}
+
+// recs[i] = grec[ids[i]] for one tile: the 64-byte records in tile-sorted order, the contiguous stream the
+// blend kernels read with cp.async.bulk.  4 lanes copy one record (coalesced 64-byte stores, gathered loads);
+// 4 independent gathers per thread in flight.
+template <int THREADS>
+__device__ __forceinline__ void gather_records(const uint32_t* ids /* shared or global */, int n,
+                                               const InstRec* __restrict__ grec, InstRec* __restrict__ recs) {
+    const float4* src = reinterpret_cast<const float4*>(grec);
+    float4* dst = reinterpret_cast<float4*>(recs);
+    const int total = 4 * n;
+    for (int q0 = threadIdx.x; q0 < total; q0 += 4 * THREADS) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int q = q0 + u * THREADS;
+            if (q < total) v[u] = __ldg(src + (size_t)ids[q >> 2] * 4 + (q & 3));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int q = q0 + u * THREADS;
+            if (q < total) dst[q] = v[u];
+        }
     }
 }
 
@@ -303,7 +347,8 @@ constexpr int SORT_LARGE_THREADS = 1024, SORT_LARGE_KEYS = 16384;    // 139 KB o
 // only if the largest tile needs it); tiles above 16384 instances sort in place in global memory.
 template <bool LARGE>
 __global__ void __launch_bounds__(LARGE ? SORT_LARGE_THREADS : SORT_SMALL_THREADS)
-tile_sort_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ keys, uint32_t* __restrict__ point_list) {
+tile_sort_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ keys, uint32_t* __restrict__ point_list,
+                 const InstRec* __restrict__ grec, InstRec* __restrict__ recs) {
     extern __shared__ uint64_t skeys[];
     const uint2 range = ranges[blockIdx.x];
     const int n = (int)(range.y - range.x);
@@ -313,28 +358,19 @@ tile_sort_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ keys, 
     if (!LARGE) {
         if (n > SORT_SMALL_KEYS) return;
         block_merge_sort<SORT_SMALL_THREADS, 8>(skeys, gk, n, ids);
+        gather_records<SORT_SMALL_THREADS>(reinterpret_cast<const uint32_t*>(skeys), n, grec, recs + range.x);
     } else {
         if (n <= SORT_SMALL_KEYS) return;
         if (n <= SORT_LARGE_KEYS) {
             block_merge_sort<SORT_LARGE_THREADS, 16>(skeys, gk, n, ids);
+            gather_records<SORT_LARGE_THREADS>(reinterpret_cast<const uint32_t*>(skeys), n, grec, recs + range.x);
         } else {
             bitonic_sort(gk, n, threadIdx.x, SORT_LARGE_THREADS);
             for (int i = threadIdx.x; i < n; i += SORT_LARGE_THREADS) ids[i] = (uint32_t)(gk[i] & 0xffffffffu);
+            __syncthreads();
+            gather_records<SORT_LARGE_THREADS>(ids, n, grec, recs + range.x);
         }
     }
-}
-
-// ---- 5. pack ----------------------------------------------------------------------------------------------
-// recs[i] = grec[point_list[i]]: the 64-byte records in tile-sorted order, so the blend kernels can
-// stream a tile's work list with one cp.async.bulk per 128 instances.  4 lanes copy one record.
-__global__ void __launch_bounds__(256) pack_records_kernel(int R, const uint32_t* __restrict__ point_list,
-                                                           const InstRec* __restrict__ grec, InstRec* __restrict__ recs) {
-    const size_t q = (size_t)blockIdx.x * 256 + threadIdx.x;
-    const size_t i = q >> 2;
-    if (i >= (size_t)R) return;
-    const int part = (int)(q & 3);
-    const uint32_t id = point_list[i];
-    reinterpret_cast<float4*>(recs + i)[part] = reinterpret_cast<const float4*>(grec + id)[part];
 }
 
 // test hook: unpack the per-Gaussian records into the reference's plain arrays; `radii` is any
@@ -359,7 +395,7 @@ __global__ void unpack_grec_kernel(int P, const InstRec* __restrict__ grec, cons
 int bin_ctas() { return BIN_CTAS; }
 
 template <bool SCATTER>
-static cudaError_t launch_bin_pass(int P, const InstRec* grec, const int* radii, int grid_x, int grid_y,
+static cudaError_t launch_bin_pass(int P, const uint4* binrec, int grid_x, int grid_y,
                                    uint32_t* matrix, const uint32_t* tile_offset, uint64_t* keys, cudaStream_t stream) {
     if (P <= 0) return cudaSuccess;
     const int num_tiles = grid_x * grid_y;
@@ -374,41 +410,40 @@ static cudaError_t launch_bin_pass(int P, const InstRec* grec, const int* radii,
             if (e != cudaSuccess) return e;
             attr_set = true;
         }
-        bin_pass_kernel<SCATTER, true><<<BIN_CTAS, BIN_THREADS, smem, stream>>>(P, chunk, grec, radii, grid_x, grid_y,
-                                                                                num_tiles, matrix, tile_offset, keys);
+        bin_pass_kernel<SCATTER, true><<<BIN_CTAS, BIN_THREADS, smem, stream>>>(P, chunk, binrec, grid_x, num_tiles, matrix,
+                                                                                tile_offset, keys);
     } else {
-        bin_pass_kernel<SCATTER, false><<<BIN_CTAS, BIN_THREADS, 0, stream>>>(P, chunk, grec, radii, grid_x, grid_y,
-                                                                              num_tiles, matrix, tile_offset, keys);
+        bin_pass_kernel<SCATTER, false><<<BIN_CTAS, BIN_THREADS, 0, stream>>>(P, chunk, binrec, grid_x, num_tiles, matrix,
+                                                                              tile_offset, keys);
     }
     return cudaGetLastError();
 }
 
-cudaError_t launch_bin_count(int P, const InstRec* grec, const int* radii, int grid_x, int grid_y, uint32_t* matrix,
-                             cudaStream_t stream) {
+cudaError_t launch_bin_count(int P, const uint4* binrec, int grid_x, int grid_y, uint32_t* matrix, cudaStream_t stream) {
     if (P <= 0) return cudaMemsetAsync(matrix, 0, (size_t)BIN_CTAS * grid_x * grid_y * sizeof(uint32_t), stream);
-    return launch_bin_pass<false>(P, grec, radii, grid_x, grid_y, matrix, nullptr, nullptr, stream);
+    return launch_bin_pass<false>(P, binrec, grid_x, grid_y, matrix, nullptr, nullptr, stream);
 }
 
 cudaError_t launch_tile_scan(int num_tiles, uint32_t* matrix, uint32_t* tile_total, uint32_t* tile_offset, uint2* ranges,
                              uint32_t* info, cudaStream_t stream) {
-    column_scan_kernel<<<(num_tiles + 255) / 256, 256, 0, stream>>>(num_tiles, BIN_CTAS, matrix, tile_total);
+    column_scan_kernel<<<(num_tiles + 31) / 32, 256, 0, stream>>>(num_tiles, BIN_CTAS, matrix, tile_total);
     tile_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(num_tiles, tile_total, tile_offset, ranges, info);
     return cudaGetLastError();
 }
 
-cudaError_t launch_bin_scatter(int P, const InstRec* grec, const int* radii, int grid_x, int grid_y, uint32_t* matrix,
+cudaError_t launch_bin_scatter(int P, const uint4* binrec, int grid_x, int grid_y, uint32_t* matrix,
                                const uint32_t* tile_offset, uint64_t* keys, cudaStream_t stream) {
-    return launch_bin_pass<true>(P, grec, radii, grid_x, grid_y, matrix, tile_offset, keys, stream);
+    return launch_bin_pass<true>(P, binrec, grid_x, grid_y, matrix, tile_offset, keys, stream);
 }
 
-int tile_sort_pack_kernel_count(int max_count) { return max_count > SORT_SMALL_KEYS ? 3 : 2; }
+int tile_sort_pack_kernel_count(int max_count) { return max_count > SORT_SMALL_KEYS ? 2 : 1; }
 
 cudaError_t launch_tile_sort_pack(int num_tiles, int max_count, int R, const uint2* ranges, uint64_t* keys,
                                   const InstRec* grec, InstRec* recs, uint32_t* point_list, cudaStream_t stream) {
     if (num_tiles <= 0 || R <= 0) return cudaSuccess;
     constexpr size_t small_smem = (size_t)(SORT_SMALL_KEYS + SORT_SMALL_KEYS / 8) * sizeof(uint64_t);
     constexpr size_t large_smem = (size_t)(SORT_LARGE_KEYS + SORT_LARGE_KEYS / 16) * sizeof(uint64_t);
-    tile_sort_kernel<false><<<num_tiles, SORT_SMALL_THREADS, small_smem, stream>>>(ranges, keys, point_list);
+    tile_sort_kernel<false><<<num_tiles, SORT_SMALL_THREADS, small_smem, stream>>>(ranges, keys, point_list, grec, recs);
     if (max_count > SORT_SMALL_KEYS) {
         static bool attr_set = false;
         if (!attr_set) {
@@ -417,10 +452,8 @@ cudaError_t launch_tile_sort_pack(int num_tiles, int max_count, int R, const uin
             if (e != cudaSuccess) return e;
             attr_set = true;
         }
-        tile_sort_kernel<true><<<num_tiles, SORT_LARGE_THREADS, large_smem, stream>>>(ranges, keys, point_list);
+        tile_sort_kernel<true><<<num_tiles, SORT_LARGE_THREADS, large_smem, stream>>>(ranges, keys, point_list, grec, recs);
     }
-    const size_t quads = (size_t)R * 4;
-    pack_records_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, stream>>>(R, point_list, grec, recs);
     return cudaGetLastError();
 }
 

@@ -97,6 +97,7 @@ struct GeomState {
     fdgs::InstRec* grec;     // [P]    per-Gaussian 64-byte record
     uint8_t* clamped;        // [P]
     uint32_t* tiles_touched; // [P]
+    uint4* binrec;           // [P] tile rectangle + depth bits of every Gaussian, for the binning passes
     size_t bytes;
     static GeomState carve(char* base, int P) {
         GeomState g;
@@ -106,6 +107,7 @@ struct GeomState {
         g.grec = c.take<fdgs::InstRec>(p);
         g.clamped = c.take<uint8_t>(p);
         g.tiles_touched = c.take<uint32_t>(p);
+        g.binrec = c.take<uint4>(p);
         g.bytes = c.total();
         return g;
     }
@@ -254,13 +256,13 @@ int fdgs_forward(const fdgs_forward_args* a, fdgs_alloc_fn geom_alloc, void* geo
         sh_staging(a->colors_precomp ? nullptr : a->shs, a->M, &pp.sh_bulk_ok, &pp.sh_row_stride_floats);
         pp.flows = a->flows_precomp;
         pp.out_means3D = a->out_means3D; pp.radii = a->radii; pp.cov3D = geom.cov3D; pp.grec = geom.grec;
-        pp.clamped = geom.clamped; pp.tiles_touched = geom.tiles_touched;
+        pp.clamped = geom.clamped; pp.tiles_touched = geom.tiles_touched; pp.binrec = geom.binrec;
         FDGS_STAGE(0, 1, fdgs::launch_preprocess_fwd(pp, stream), "preprocess_fwd");
     }
     // binning: per-tile counts, offsets, ranges and the total instance count R
     FDGS_STAGE(1, (P > 0 ? 1 : 0) + 2,
                [&]() {
-                   cudaError_t e = fdgs::launch_bin_count(P, geom.grec, a->radii, grid_x, grid_y, img.bin_matrix, stream);
+                   cudaError_t e = fdgs::launch_bin_count(P, geom.binrec, grid_x, grid_y, img.bin_matrix, stream);
                    if (e != cudaSuccess) return e;
                    return fdgs::launch_tile_scan((int)img.tiles, img.bin_matrix, img.tile_total, img.tile_offset, img.ranges,
                                                  img.bin_info, stream);
@@ -282,8 +284,7 @@ int fdgs_forward(const fdgs_forward_args* a, fdgs_alloc_fn geom_alloc, void* geo
     res->binning_bytes = bin_bytes;
 
     if (num_rendered > 0) {
-        FDGS_STAGE(2, 1, fdgs::launch_bin_scatter(P, geom.grec, a->radii, grid_x, grid_y, img.bin_matrix, img.tile_offset,
-                                                  bin.keys, stream),
+        FDGS_STAGE(2, 1, fdgs::launch_bin_scatter(P, geom.binrec, grid_x, grid_y, img.bin_matrix, img.tile_offset, bin.keys, stream),
                    "bin_scatter");
         FDGS_STAGE(3, fdgs::tile_sort_pack_kernel_count(bin_info[1]),
                    fdgs::launch_tile_sort_pack((int)img.tiles, bin_info[1], num_rendered, img.ranges, bin.keys, geom.grec, bin.recs,

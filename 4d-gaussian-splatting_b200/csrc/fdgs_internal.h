@@ -41,18 +41,19 @@ struct PreprocessFwdParams {
     InstRec* grec;          // [P] the 64-byte record every tile instance of the Gaussian copies
     uint8_t* clamped;       // bit ch set = channel ch was clamped at 0
     uint32_t* tiles_touched;
+    uint4* binrec;          // [P] compact bin record of EVERY Gaussian (see launch_bin_count)
 };
 cudaError_t launch_preprocess_fwd(const PreprocessFwdParams& p, cudaStream_t stream);
 
 // ---- binning -----------------------------------------------------------------------------------
 // counting sort of the (Gaussian, tile) instances by tile, BIN_CTAS persistent CTAs (binning.cu)
 int bin_ctas();                                 // rows of the [bin_ctas()][num_tiles] count matrix
-cudaError_t launch_bin_count(int P, const InstRec* grec, const int* radii, int grid_x, int grid_y, uint32_t* matrix,
-                             cudaStream_t stream);
+// binrec[i] = { x0 | y0 << 16, x1 | y1 << 16, depth bits, 0 }: tile rectangle (empty = not rendered) of Gaussian i
+cudaError_t launch_bin_count(int P, const uint4* binrec, int grid_x, int grid_y, uint32_t* matrix, cudaStream_t stream);
 // matrix -> per-CTA column prefixes; tile_offset / ranges; info[0] = total instances R, info[1] = largest tile
 cudaError_t launch_tile_scan(int num_tiles, uint32_t* matrix, uint32_t* tile_total, uint32_t* tile_offset, uint2* ranges,
                              uint32_t* info, cudaStream_t stream);
-cudaError_t launch_bin_scatter(int P, const InstRec* grec, const int* radii, int grid_x, int grid_y, uint32_t* matrix,
+cudaError_t launch_bin_scatter(int P, const uint4* binrec, int grid_x, int grid_y, uint32_t* matrix,
                                const uint32_t* tile_offset, uint64_t* keys, cudaStream_t stream);
 // sorts every tile's keys and writes the 64-byte instance records + the sorted index list
 int tile_sort_pack_kernel_count(int max_count);

@@ -318,7 +318,7 @@ __device__ __forceinline__ void mat3_mul(const float A[3][3], const float B[3][3
 }
 
 // ---- geometry backward ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(GB_THREADS) geom_bwd_kernel(const PreprocessBwdParams a, const int has_sh_part) {
+__global__ void __launch_bounds__(GB_THREADS, 6) geom_bwd_kernel(const PreprocessBwdParams a, const int has_sh_part) {
     const int idx = blockIdx.x * GB_THREADS + threadIdx.x;
     if (idx >= a.P) return;
     const bool vis = (a.radii[idx] > 0) && (a.tiles_touched[idx] != 0u);

@@ -8,9 +8,9 @@
 // B200 design:
 //   * geometry inputs (68 B/Gaussian) are read with coalesced 32/128-bit loads;
 //   * the 12*M-byte SH row of every *visible* Gaussian is streamed global->shared with one
-//     cp.async.bulk (TMA 1-D, SASS UBLKCP) per row, all rows of a block completing on one
-//     mbarrier; rows sit at a padded 16-byte-aligned stride so that the per-thread LDS.128
-//     reads are bank-conflict free; no register staging, no 12-byte strided LDG;
+//     cp.async.bulk (TMA 1-D, SASS UBLKCP) per row into a compacted slot, all rows of a round
+//     completing on one mbarrier; slots sit at a padded 16-byte-aligned stride so that the
+//     per-thread LDS.128 reads are bank-conflict free; no register staging, no 12-byte strided LDG;
 //   * out_means3D is written for every Gaussian here (the reference clones means3D first,
 //     rasterize_points.cu:85, and overwrites the time-visible rows).
 // All arithmetic that feeds radii / tiles / depth / conic / rgb follows the reference bit for
@@ -22,6 +22,7 @@ namespace fdgs {
 namespace {
 
 constexpr int PRE_THREADS = 128;
+constexpr int PRE_CAP = 48;       // shared-memory SH row slots per CTA (rendered rows per round)
 
 struct ShBasis {
     float l[16];   // l0m0, l1m1, l1m0, l1p1, l2m2 .. l3p3
@@ -174,9 +175,10 @@ __device__ __forceinline__ void sh_color_3d(const Row& row, int M, int deg, floa
 }
 
 template <bool BULK>
-__global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreprocessFwdParams a) {
+__global__ void __launch_bounds__(PRE_THREADS, 5) preprocess_fwd_kernel(const PreprocessFwdParams a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
+    __shared__ int warp_cnt[PRE_THREADS / 32];
 
     const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
     const bool in_range = idx < a.P;
@@ -313,37 +315,52 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const Prepr
     uint8_t clamp_bits = 0;
     if (need_sh) {
         const int row_floats = 3 * a.M;
-        if (BULK) {
-            const int nvis = __syncthreads_count(visible);
-            float* rows = reinterpret_cast<float*>(smem_raw);
-            const int stride = a.sh_row_stride_floats;   // padded, multiple of 4
-            if (threadIdx.x == 0 && nvis > 0) mbar_expect_tx(&bar, (uint32_t)nvis * (uint32_t)row_floats * 4u);
-            if (visible)
-                bulk_g2s(rows + (size_t)threadIdx.x * stride, a.shs + (size_t)idx * row_floats,
-                         (uint32_t)row_floats * 4u, &bar);
-            if (visible) mbar_wait(&bar, 0);
-        }
-        if (visible) {
+        auto eval = [&](auto row) {
             const float dx = fsub(ox, a.cam_pos[0]), dy = fsub(oy, a.cam_pos[1]), dz = fsub(oz, a.cam_pos[2]);
             const float len = fsqrt(ffma(dz, dz, ffma(dx, dx, fmul(dy, dy))));
             const float x = fdiv(dx, len), y = fdiv(dy, len), z = fdiv(dz, len);
             const bool sh3d = (a.gaussian_dim == 3) || a.force_sh_3d;
-            if (BULK) {
-                RowSmem row{reinterpret_cast<const float4*>(reinterpret_cast<float*>(smem_raw) +
-                                                            (size_t)threadIdx.x * a.sh_row_stride_floats)};
-                if (sh3d) sh_color_3d(row, a.M, a.D, x, y, z, rgb);
-                else sh_color_4d(row, a.M, a.D, a.D_t, x, y, z, fsub(a.ts[idx], a.timestamp), a.time_duration, rgb);
-            } else {
-                RowGmem row{a.shs + (size_t)idx * row_floats};
-                if (sh3d) sh_color_3d(row, a.M, a.D, x, y, z, rgb);
-                else sh_color_4d(row, a.M, a.D, a.D_t, x, y, z, fsub(a.ts[idx], a.timestamp), a.time_duration, rgb);
-            }
+            if (sh3d) sh_color_3d(row, a.M, a.D, x, y, z, rgb);
+            else sh_color_4d(row, a.M, a.D, a.D_t, x, y, z, fsub(a.ts[idx], a.timestamp), a.time_duration, rgb);
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
                 const float r = fadd(rgb[ch], 0.5f);
                 if (r < 0.f) { clamp_bits |= (1u << ch); rgb[ch] = 0.f; }
                 else rgb[ch] = r;
             }
+        };
+        if (BULK) {
+            // Only the rows of RENDERED Gaussians are fetched, into PRE_CAP shared-memory slots handed out by a
+            // block-level compaction (typically a third of a CTA's Gaussians are rendered): a third of the
+            // shared memory of a slot-per-thread layout, so twice the CTAs per SM stay resident to hide the
+            // latency of the fp32/fp64 chain above.  More rendered rows than slots -> another round.
+            const unsigned bal = __ballot_sync(0xffffffffu, visible);
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            if (lane == 0) warp_cnt[warp] = __popc(bal);
+            __syncthreads();
+            int base = 0, nvis = 0;
+#pragma unroll
+            for (int w = 0; w < PRE_THREADS / 32; ++w) {
+                if (w < warp) base += warp_cnt[w];
+                nvis += warp_cnt[w];
+            }
+            const int my_rank = base + __popc(bal & ((1u << lane) - 1u));
+            float* rows = reinterpret_cast<float*>(smem_raw);
+            const int stride = a.sh_row_stride_floats;   // padded, multiple of 4
+            for (int round = 0, lo = 0; lo < nvis; ++round, lo += PRE_CAP) {
+                const int cnt = min(PRE_CAP, nvis - lo);
+                const bool mine = visible && my_rank >= lo && my_rank < lo + cnt;
+                if (round > 0) __syncthreads();   // the previous round's readers are done with the slots
+                if (threadIdx.x == 0) mbar_expect_tx(&bar, (uint32_t)cnt * (uint32_t)row_floats * 4u);
+                if (mine) {
+                    float* slot = rows + (size_t)(my_rank - lo) * stride;
+                    bulk_g2s(slot, a.shs + (size_t)idx * row_floats, (uint32_t)row_floats * 4u, &bar);
+                    mbar_wait(&bar, (uint32_t)round & 1u);
+                    eval(RowSmem{reinterpret_cast<const float4*>(slot)});
+                }
+            }
+        } else if (visible) {
+            eval(RowGmem{a.shs + (size_t)idx * row_floats});
         }
     } else if (visible) {
         rgb[0] = a.colors_precomp[3 * idx + 0];
@@ -354,6 +371,10 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const Prepr
     if (in_range) {
         a.radii[idx] = visible ? radius : 0;
         a.tiles_touched[idx] = visible ? tiles : 0u;
+        // compact record for the binning passes: tile rectangle (empty when not rendered) + depth bits
+        a.binrec[idx] = visible ? make_uint4((uint32_t)rx0 | ((uint32_t)ry0 << 16), (uint32_t)rx1 | ((uint32_t)ry1 << 16),
+                                             __float_as_uint(depth), 0u)
+                                : make_uint4(0u, 0u, 0u, 0u);
         if (visible) {
             a.clamped[idx] = clamp_bits;
             // The 64-byte record every (tile, Gaussian) instance copies (binning.cu).  Besides the
@@ -392,7 +413,7 @@ cudaError_t launch_preprocess_fwd(const PreprocessFwdParams& p, cudaStream_t str
     const int blocks = (p.P + PRE_THREADS - 1) / PRE_THREADS;
     const bool bulk = p.sh_bulk_ok && p.colors_precomp == nullptr;
     if (bulk) {
-        const size_t smem = (size_t)PRE_THREADS * p.sh_row_stride_floats * sizeof(float);
+        const size_t smem = (size_t)PRE_CAP * p.sh_row_stride_floats * sizeof(float);
         static bool attr_set = false;
         if (!attr_set) {
             cudaError_t e = cudaFuncSetAttribute(preprocess_fwd_kernel<true>,

@@ -8,7 +8,8 @@ view of the synthetic scene of SURVEY.md section 8(d), through the reference-fac
 
   value   inputs resident in HBM, CUDA events, K steps after W warm-ups, max over ranks
   e2e     same call with HOST buffers: per step the camera matrices and the upstream gradient image
-          are copied host->device from pinned memory and the loss is read back device->host
+          are copied host->device from pinned memory (the image on a copy stream, overlapping the
+          forward, both arms alike) and the loss is read back device->host
   N > 1   one view per rank (weak scaling), replicated Gaussians, SUM all-reduce (NCCL) of the
           per-Gaussian parameter gradients + the densification statistics inside the step
   --impl reference   the UNMODIFIED reference CUDA rasterizer (oracle/_ref, built from
@@ -144,6 +145,7 @@ class Runner:
             import ref_api
             self.ref_api = ref_api
         self.G_dev = wl.G_host.to(wl.device)
+        self.copy_stream = torch.cuda.Stream(device=wl.device)
         self.last = None
 
     def _raster(self, settings):
@@ -176,8 +178,16 @@ class Runner:
         st = dict(wl.settings)
         for k, h in wl.cam_host.items():
             st[k] = h.to(wl.device, non_blocking=True)
-        G = wl.G_host.to(wl.device, non_blocking=True)
+        # the upstream gradient image (the stand-in for the ground-truth image of a training step) is
+        # uploaded on a copy stream while the forward runs, like a data loader prefetching the next view
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(self.copy_stream):
+            G = wl.G_host.to(wl.device, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self.copy_stream)
         (color, radii, depth, alpha, flow, covs), means2D = self._raster(st)
+        cur.wait_event(ready)
+        G.record_stream(cur)
         loss = (color * G).sum()
         loss.backward()
         self.last = (loss, radii, means2D)
