@@ -369,6 +369,30 @@ int fdgs_mark_visible(int P, const float* means3D, const float* viewmatrix, cons
     return FDGS_OK;
 }
 
+static int pack_common(bool unpack, int n, float* const* tensors, const int* widths, const long long* block_off,
+                       const long long* idx, long long K, float* flat, void* stream_v) {
+    g_last_error.clear();
+    if (n < 0 || n > FDGS_MAX_PACK || K < 0) return fail(FDGS_ERR_INVALID_ARG, "bad tensor count / row count");
+    if (n == 0 || K == 0) return FDGS_OK;
+    if (!tensors || !widths || !block_off || !idx || !flat) return fail(FDGS_ERR_INVALID_ARG, "null argument");
+    for (int i = 0; i < n; ++i)
+        if (!tensors[i] || widths[i] <= 0 || block_off[i] < 0) return fail(FDGS_ERR_INVALID_ARG, "bad tensor table entry");
+    FDGS_CUDA(fdgs::launch_pack_rows(unpack, n, tensors, widths, block_off, idx, K, flat, reinterpret_cast<cudaStream_t>(stream_v)),
+              unpack ? "unpack_rows" : "pack_rows");
+    g_kernel_launches += 1;
+    return FDGS_OK;
+}
+
+int fdgs_pack_rows(int n, const float* const* tensors, const int* widths, const long long* block_off, const long long* idx,
+                   long long K, float* flat, void* stream) {
+    return pack_common(false, n, const_cast<float* const*>(tensors), widths, block_off, idx, K, flat, stream);
+}
+
+int fdgs_unpack_rows(int n, float* const* tensors, const int* widths, const long long* block_off, const long long* idx,
+                     long long K, const float* flat, void* stream) {
+    return pack_common(true, n, tensors, widths, block_off, idx, K, const_cast<float*>(flat), stream);
+}
+
 int fdgs_profile_enable(int on) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof_on = on != 0;

@@ -145,6 +145,9 @@ struct PreprocessBwdParams {
 cudaError_t launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream);
 int preprocess_bwd_kernel_count(const PreprocessBwdParams& p);
 
+cudaError_t launch_pack_rows(bool unpack, int n, float* const* tensors, const int* widths, const long long* block_off,
+                             const long long* idx, long long K, float* flat, cudaStream_t stream);
+
 cudaError_t launch_mark_visible(int P, const float* means3D, const float* viewmatrix, unsigned char* present,
                                 cudaStream_t stream);
 

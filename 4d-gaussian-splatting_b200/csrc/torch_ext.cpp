@@ -22,6 +22,7 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
 #include <tuple>
+#include <vector>
 #include "../../include/fdgs.h"
 
 namespace {
@@ -250,7 +251,63 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> DebugExportBinning(const
     return std::make_tuple(point_list, ranges, n_contrib);
 }
 
+// Multi-GPU exchange: gather the rows `idx` of every gradient tensor into one flat buffer (one block of K rows
+// per tensor, 16-byte aligned block starts) / scatter the reduced rows back.  See fdgs/dist.py.
+static std::vector<long long> block_offsets(const std::vector<torch::Tensor>& ts, long long K, std::vector<int>& widths,
+                                            long long& total) {
+    std::vector<long long> off;
+    total = 0;
+    for (const auto& t : ts) {
+        TORCH_CHECK(t.is_cuda() && t.scalar_type() == torch::kFloat32 && t.is_contiguous() && t.dim() >= 1,
+                    "fdgs: gradient tensors must be contiguous float32 CUDA tensors");
+        const long long w = t.size(0) > 0 ? t.numel() / t.size(0) : 0;
+        TORCH_CHECK(w > 0, "fdgs: empty gradient tensor");
+        widths.push_back((int)w);
+        off.push_back(total);
+        total += (K * w + 3) / 4 * 4;
+    }
+    return off;
+}
+
+torch::Tensor PackRows(std::vector<torch::Tensor> tensors, const torch::Tensor& idx) {
+    TORCH_CHECK((int)tensors.size() <= FDGS_MAX_PACK, "fdgs: too many tensors");
+    TORCH_CHECK(idx.is_cuda() && idx.scalar_type() == torch::kInt64 && idx.is_contiguous(), "fdgs: idx must be int64 CUDA");
+    const long long K = idx.numel();
+    std::vector<int> widths;
+    long long total = 0;
+    std::vector<long long> off = block_offsets(tensors, K, widths, total);
+    torch::Tensor flat = torch::empty({total}, idx.options().dtype(torch::kFloat32));
+    if (K == 0 || tensors.empty()) return flat;
+    const c10::cuda::CUDAGuard guard(idx.device());
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream().stream();
+    std::vector<const float*> ptr;
+    for (const auto& t : tensors) ptr.push_back(t.data_ptr<float>());
+    check(fdgs_pack_rows((int)tensors.size(), ptr.data(), widths.data(), off.data(), reinterpret_cast<const long long*>(idx.data_ptr<int64_t>()), K,
+                         flat.data_ptr<float>(), (void*)stream),
+          "pack_rows");
+    return flat;
+}
+
+void UnpackRows(const torch::Tensor& flat, std::vector<torch::Tensor> tensors, const torch::Tensor& idx) {
+    TORCH_CHECK((int)tensors.size() <= FDGS_MAX_PACK, "fdgs: too many tensors");
+    const long long K = idx.numel();
+    std::vector<int> widths;
+    long long total = 0;
+    std::vector<long long> off = block_offsets(tensors, K, widths, total);
+    TORCH_CHECK(flat.numel() == total && flat.is_contiguous() && flat.scalar_type() == torch::kFloat32, "fdgs: flat buffer mismatch");
+    if (K == 0 || tensors.empty()) return;
+    const c10::cuda::CUDAGuard guard(idx.device());
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream().stream();
+    std::vector<float*> ptr;
+    for (auto& t : tensors) ptr.push_back(t.data_ptr<float>());
+    check(fdgs_unpack_rows((int)tensors.size(), ptr.data(), widths.data(), off.data(), reinterpret_cast<const long long*>(idx.data_ptr<int64_t>()), K,
+                           flat.data_ptr<float>(), (void*)stream),
+          "unpack_rows");
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+    m.def("pack_rows", &PackRows);
+    m.def("unpack_rows", &UnpackRows);
     m.def("rasterize_gaussians", &RasterizeGaussiansCUDA);
     m.def("rasterize_gaussians_backward", &RasterizeGaussiansBackwardCUDA);
     m.def("mark_visible", &markVisible);

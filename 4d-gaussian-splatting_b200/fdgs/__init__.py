@@ -22,7 +22,7 @@ EXT_PATH = os.path.join(LIB_DIR, "fdgs_C.so")
 ABI_SYMBOLS = (
     "fdgs_version", "fdgs_last_error", "fdgs_geom_bytes", "fdgs_image_bytes", "fdgs_binning_bytes",
     "fdgs_forward", "fdgs_backward", "fdgs_mark_visible", "fdgs_debug_export_geom", "fdgs_debug_export_binning",
-    "fdgs_profile_enable", "fdgs_profile_read", "fdgs_launch_count",
+    "fdgs_profile_enable", "fdgs_profile_read", "fdgs_launch_count", "fdgs_pack_rows", "fdgs_unpack_rows",
 )
 
 STAGE_NAMES = ("preprocess_fwd", "bin_count_scan", "bin_scatter", "tile_sort_pack", "reserved", "blend_fwd", "blend_bwd",

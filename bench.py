@@ -11,7 +11,8 @@ view of the synthetic scene of SURVEY.md section 8(d), through the reference-fac
           are copied host->device from pinned memory (the image on a copy stream, overlapping the
           forward, both arms alike) and the loss is read back device->host
   N > 1   one view per rank (weak scaling), replicated Gaussians, SUM all-reduce (NCCL) of the
-          per-Gaussian parameter gradients + the densification statistics inside the step
+          per-Gaussian parameter gradients (rows of the union of the ranks' rendered Gaussians, one flat
+          buffer) + the densification statistics inside the step
   --impl reference   the UNMODIFIED reference CUDA rasterizer (oracle/_ref, built from
           /root/reference by oracle/build_ref.py) on the same workload, same metric; if that .so did
           not travel, the CPU oracle port on a bounded sample.  Rank 0 only.
@@ -307,11 +308,14 @@ def main():
     if eff_world > 1:
         from fdgs.dist import allreduce_gradients, ViewBatchStats
 
+        dense = os.environ.get("FDGS_DENSE_ALLREDUCE") is not None
+
         def sync_grads():
-            allreduce_gradients(runner.grads())
             stats = ViewBatchStats(wl.P, device)
             stats.add_view(runner.last[2].grad, runner.last[1])
             stats.reduce()
+            # rows of Gaussians no rank rendered are zero everywhere: exchange the union's rows only
+            allreduce_gradients(runner.grads(), union_visible=None if dense else stats.max_radii > 0)
     else:
         def sync_grads():
             return None

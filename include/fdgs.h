@@ -193,6 +193,16 @@ int fdgs_backward(const fdgs_backward_args* args, void* stream);
 int fdgs_mark_visible(int P, const float* means3D, const float* viewmatrix,
                       const float* projmatrix, unsigned char* present, void* stream);
 
+/* Multi-GPU gradient exchange helpers (new: the reference has no multi-GPU path; it sums the gradients of
+ * sequential views, train.py:104-166).  pack: flat[block_off[t] + r*width[t] + c] = tensors[t][idx[r]*width[t] + c]
+ * for r < K; unpack: the inverse scatter.  `tensors` / `widths` / `block_off` are HOST arrays of n <=
+ * FDGS_MAX_PACK entries, `idx` (sorted row indices, int64) and `flat` are device pointers. */
+#define FDGS_MAX_PACK 16
+int fdgs_pack_rows(int n, const float* const* tensors, const int* widths, const long long* block_off,
+                   const long long* idx, long long K, float* flat, void* stream);
+int fdgs_unpack_rows(int n, float* const* tensors, const int* widths, const long long* block_off,
+                     const long long* idx, long long K, const float* flat, void* stream);
+
 /* Test/diagnostic hooks (used by tests/ and bench.py only): copy private
  * per-Gaussian / per-instance state out of the scratch buffers into plain
  * caller-provided device arrays so that parity tests can compare them with the

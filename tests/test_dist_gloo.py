@@ -88,3 +88,40 @@ def test_two_ranks_match_the_sequential_loop(num_views):
         assert torch.equal(vc, ref_stats.visibility_count)                        # SUM
         assert torch.equal(mr, ref_stats.max_radii)                               # MAX
     assert out[0][5] == pytest.approx(out[1][5])
+
+
+def _sparse_worker(rank, world, port, P, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(7 + rank)
+        vis = torch.rand(P, generator=g) < 0.3                      # this rank's rendered Gaussians
+        grads = [torch.randn(P, 3, generator=g) * vis[:, None], torch.randn(P, 5, 3, generator=g) * vis[:, None, None],
+                 None, torch.randn(P, 1, generator=g) * vis[:, None]]
+        dense = [None if x is None else x.clone() for x in grads]
+        union = vis.to(torch.int32)
+        dist.all_reduce(union, op=dist.ReduceOp.MAX)
+        fdist.allreduce_gradients(grads, union_visible=union > 0)    # sparse exchange
+        fdist.allreduce_gradients(dense)                            # dense exchange
+        same = all(torch.equal(a, b) for a, b in zip(grads, dense) if a is not None)
+        # above the density threshold the sparse call must take the dense path and still be right
+        g2 = [x.clone() for x in dense if x is not None]
+        fdist.allreduce_gradients(g2, union_visible=torch.ones(P, dtype=torch.bool), dense_above=0.5)
+        out[rank] = (same, float((union > 0).float().mean()), all(torch.allclose(a, world * b) for a, b in zip(g2, [x for x in dense if x is not None])))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sparse_union_allreduce_equals_dense():
+    """The union-of-visibility exchange (one flat buffer over the rendered rows) gives bit-identical sums to
+    the dense all-reduce: rows outside the union are zero on every rank."""
+    world, P = 2, 1000
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_sparse_worker, args=(world, _free_port(), P, out), nprocs=world, join=True)
+    assert len(out) == world
+    for r in range(world):
+        same, frac, dense_ok = out[r]
+        assert same and dense_ok
+        assert 0.3 < frac < 0.6

@@ -486,3 +486,28 @@ def test_render_python_preprocess_flags(C):
     agree = (a["radii"] > 0) == (b["radii"] > 0)
     assert float(agree.float().mean()) > 0.995
     assert helpers.psnr(helpers.to_np(a["render"]), helpers.to_np(b["render"])) > 35.0
+
+
+def test_pack_unpack_rows_exchange_kernels(C):
+    """csrc/exchange.cu (multi-GPU gradient exchange): gather of the union's rows into one flat buffer and the
+    inverse scatter, bit-exact against torch indexing, vector (row % 16 B == 0) and scalar paths, ragged K."""
+    g = torch.Generator(device=DEV).manual_seed(3)
+    P = 10007
+    tensors = [torch.randn(P, 3, device=DEV, generator=g), torch.randn(P, 48, 3, device=DEV, generator=g),
+               torch.randn(P, 1, device=DEV, generator=g), torch.randn(P, 4, device=DEV, generator=g)]
+    mask = torch.rand(P, device=DEV, generator=g) < 0.37
+    idx = torch.nonzero(mask).squeeze(1)
+    K = idx.numel()
+    flat = C.pack_rows(tensors, idx)
+    off = 0
+    for t in tensors:
+        w = t.numel() // P
+        assert torch.equal(flat[off:off + K * w].view(K, w), t.view(P, w)[idx])
+        off += (K * w + 3) // 4 * 4
+    assert off == flat.numel()
+    outs = [torch.zeros_like(t) for t in tensors]
+    C.unpack_rows(flat, outs, idx)
+    for o, t in zip(outs, tensors):
+        assert torch.equal(o, t * mask.view(P, *([1] * (t.dim() - 1))))
+    empty = torch.empty(0, dtype=torch.int64, device=DEV)
+    assert C.pack_rows(tensors, empty).numel() == 0
