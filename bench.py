@@ -376,9 +376,15 @@ def main():
         ach = alg / (stage_ms[dom] * 1e-3) / 1e9
         b_fwd = 84.0 * wl.P + 719.0 * P_vis + 88.0 * R + 32.0 * N
         b_bwd = 52.0 * R + 36.0 * N + 1428.0 * P_vis
+        traffic = None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of that kernel, per launch, from the committed ncu capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[dom]
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src,
-                    "note": "dominant kernel is instruction-issue bound, not HBM bound (see profiles/)",
+                    "traffic": traffic, "algorithmic_bytes": alg, "peak_source": peak_src,
+                    "note": "dominant kernel is instruction-issue / shared-memory bound, not HBM bound (profiles/r01_blend_ncu_v8.md)",
                     "frame": {"algorithmic_bytes": b_fwd + b_bwd, "achieved": (b_fwd + b_bwd) / (ms_step * 1e-3) / 1e9,
                               "frac": (b_fwd + b_bwd) / (ms_step * 1e-3) / 1e9 / peak}}
 

@@ -29,7 +29,7 @@ if has launches; then
 fi
 if has full; then
   # skip the warm-up launches of each kernel (-s counts matching launches only), capture one of each
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'blend_(fwd|bwd)_kernel' -s 6 -c 2 \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'blend_(fwd|bwd|bwd2)_kernel' -s 6 -c 2 \
       -f -o $OUT/${TAG}_blend python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_full.log 2>&1
   ls -la $OUT/${TAG}_blend.ncu-rep
 fi
