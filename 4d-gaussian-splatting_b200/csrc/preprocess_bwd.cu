@@ -218,18 +218,16 @@ __global__ void __launch_bounds__(SB_THREADS, 4) sh_bwd_kernel(const PreprocessB
     slot_of[tid] = (short)my_rank;
     __syncthreads();
 
-    // zero rows: every float4 of every non-rendered row of this CTA, coalesced.  Called AFTER the first round's
-    // row loads have been issued, so the stores go out while those loads are in flight.
-    auto write_zero_rows = [&]() {
+    // zero rows: every float4 of every non-rendered row of this CTA, coalesced
+    {
         const int rows_here = min(SB_THREADS, a.P - blockIdx.x * SB_THREADS);
+        float4* dst = reinterpret_cast<float4*>(a.dL_dsh + (size_t)blockIdx.x * SB_THREADS * row_floats);
+        const int total = rows_here * nq;
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         if (BULK) {
-            // warp w takes the rows w, w + 4, ...: one row = nq float4, lanes cover it in ceil(nq / 32) stores
-            float4* base = reinterpret_cast<float4*>(a.dL_dsh + (size_t)blockIdx.x * SB_THREADS * row_floats);
-            for (int r = warp; r < rows_here; r += SB_THREADS / 32) {
-                if (slot_of[r] >= 0) continue;
-                float4* dst = base + (size_t)r * nq;
-                for (int f = lane; f < nq; f += 32) dst[f] = z;
+            for (int f = tid; f < total; f += SB_THREADS) {
+                const int r = f / nq;
+                if (slot_of[r] < 0) dst[f] = z;
             }
         } else {
             // generic path (row not a multiple of 16 bytes): scalar stores
@@ -237,7 +235,7 @@ __global__ void __launch_bounds__(SB_THREADS, 4) sh_bwd_kernel(const PreprocessB
             for (int f = tid; f < rows_here * row_floats; f += SB_THREADS)
                 if (slot_of[f / row_floats] < 0) d1[f] = 0.f;
         }
-    };
+    }
 
     ShCtx c;
     if (vis) sh_ctx_init(a, idx, c);
@@ -255,7 +253,6 @@ __global__ void __launch_bounds__(SB_THREADS, 4) sh_bwd_kernel(const PreprocessB
             }
             if (tid == 0) mbar_expect_tx(&bar, (uint32_t)cnt * (uint32_t)row_floats * 4u);
             if (mine) bulk_g2s(rowq, a.shs + (size_t)idx * row_floats, (uint32_t)row_floats * 4u, &bar);
-            if (round == 0) write_zero_rows();
             if (mine) {
                 mbar_wait(&bar, (uint32_t)round & 1u);
                 float ddx, ddy, ddz, dtt;
@@ -270,12 +267,8 @@ __global__ void __launch_bounds__(SB_THREADS, 4) sh_bwd_kernel(const PreprocessB
                 a.dL_dts[idx] = c.sh4d ? dtt : 0.f;
             }
         }
-        if (nvis == 0) write_zero_rows();
         if (vis) bulk_wait_all();
-    } else {
-        write_zero_rows();
-    }
-    if (!BULK && vis) {
+    } else if (vis) {
         // generic path: global loads / stores, one coefficient at a time
         const float* grow = a.shs + (size_t)idx * row_floats;
         float* drow = a.dL_dsh + (size_t)idx * row_floats;
@@ -325,7 +318,7 @@ __device__ __forceinline__ void mat3_mul(const float A[3][3], const float B[3][3
 }
 
 // ---- geometry backward ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(GB_THREADS, 6) geom_bwd_kernel(const PreprocessBwdParams a, const int has_sh_part) {
+__global__ void __launch_bounds__(GB_THREADS, 8) geom_bwd_kernel(const PreprocessBwdParams a, const int has_sh_part) {
     const int idx = blockIdx.x * GB_THREADS + threadIdx.x;
     if (idx >= a.P) return;
     const bool vis = (a.radii[idx] > 0) && (a.tiles_touched[idx] != 0u);
