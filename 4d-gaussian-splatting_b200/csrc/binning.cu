@@ -288,16 +288,22 @@ __device__ __forceinline__ void block_merge_sort(uint64_t* sm, const uint64_t* _
 // 4 independent gathers per thread in flight.
 template <int THREADS>
 __device__ __forceinline__ void gather_records(const uint32_t* ids /* shared or global */, int n,
-                                               const InstRec* __restrict__ grec, InstRec* __restrict__ recs) {
+                                               const InstRec* __restrict__ grec, StageRec* __restrict__ recs) {
     const float4* src = reinterpret_cast<const float4*>(grec);
-    float4* dst = reinterpret_cast<float4*>(recs);
-    const int total = 4 * n;
+    float4* dst = reinterpret_cast<float4*>(recs);   // 5 float4 per staged record, the fifth is padding
+    // thread q writes the q-th float4 of the tile's output stream: fully coalesced stores; 4 of every 5
+    // consecutive threads read the 4 planes of one gathered record (one 64-byte line)
+    const int total = 5 * n;
     for (int q0 = threadIdx.x; q0 < total; q0 += 4 * THREADS) {
         float4 v[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int q = q0 + u * THREADS;
-            if (q < total) v[u] = __ldg(src + (size_t)ids[q >> 2] * 4 + (q & 3));
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q < total) {
+                const int i = q / 5, part = q - 5 * i;
+                if (part < 4) v[u] = __ldg(src + (size_t)ids[i] * 4 + part);
+            }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -348,7 +354,7 @@ constexpr int SORT_LARGE_THREADS = 1024, SORT_LARGE_KEYS = 16384;    // 139 KB o
 template <bool LARGE>
 __global__ void __launch_bounds__(LARGE ? SORT_LARGE_THREADS : SORT_SMALL_THREADS)
 tile_sort_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ keys, uint32_t* __restrict__ point_list,
-                 const InstRec* __restrict__ grec, InstRec* __restrict__ recs) {
+                 const InstRec* __restrict__ grec, StageRec* __restrict__ recs) {
     extern __shared__ uint64_t skeys[];
     const uint2 range = ranges[blockIdx.x];
     const int n = (int)(range.y - range.x);
@@ -439,7 +445,7 @@ cudaError_t launch_bin_scatter(int P, const uint4* binrec, int grid_x, int grid_
 int tile_sort_pack_kernel_count(int max_count) { return max_count > SORT_SMALL_KEYS ? 2 : 1; }
 
 cudaError_t launch_tile_sort_pack(int num_tiles, int max_count, int R, const uint2* ranges, uint64_t* keys,
-                                  const InstRec* grec, InstRec* recs, uint32_t* point_list, cudaStream_t stream) {
+                                  const InstRec* grec, StageRec* recs, uint32_t* point_list, cudaStream_t stream) {
     if (num_tiles <= 0 || R <= 0) return cudaSuccess;
     constexpr size_t small_smem = (size_t)(SORT_SMALL_KEYS + SORT_SMALL_KEYS / 8) * sizeof(uint64_t);
     constexpr size_t large_smem = (size_t)(SORT_LARGE_KEYS + SORT_LARGE_KEYS / 16) * sizeof(uint64_t);

@@ -28,7 +28,7 @@ constexpr int BB_BATCH = 128;
 constexpr int BB_STAGES = 3;
 
 struct __align__(128) BlendBwdSmem {
-    InstRec recs[BB_STAGES][BB_BATCH];
+    StageRec recs[BB_STAGES][BB_BATCH];
     uint64_t full[BB_STAGES];
     uint64_t empty[BB_STAGES];
     unsigned int nmax;
@@ -73,14 +73,14 @@ __global__ void __launch_bounds__(BB_THREADS, AUX ? 3 : 4) blend_bwd_kernel(cons
     // entries at list positions >= max n_contrib are skipped by every pixel (backward.cu:1040)
     const int n = min(n_list, (int)sm.nmax);
     const int nb = (n + BB_BATCH - 1) / BB_BATCH;
-    const InstRec* src = p.recs + range.x;
+    const StageRec* src = p.recs + range.x;
 
     int issued = 0;
     if (threadIdx.x == 0) {
         for (; issued < nb && issued < BB_STAGES; ++issued) {
             const int hi = n - issued * BB_BATCH, lo = max(0, hi - BB_BATCH);
-            mbar_expect_tx(&sm.full[issued], (uint32_t)(hi - lo) * 64u);
-            bulk_g2s(&sm.recs[issued][0], src + lo, (uint32_t)(hi - lo) * 64u, &sm.full[issued]);
+            mbar_expect_tx(&sm.full[issued], (uint32_t)(hi - lo) * kStageRecBytes);
+            bulk_g2s(&sm.recs[issued][0], src + lo, (uint32_t)(hi - lo) * kStageRecBytes, &sm.full[issued]);
         }
     }
 
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(BB_THREADS, AUX ? 3 : 4) blend_bwd_kernel(cons
         const int hi = n - b * BB_BATCH, lo = max(0, hi - BB_BATCH), cnt = hi - lo;
         mbar_wait(&sm.full[s], ph);
         if ((unsigned)lo < wmax) {
-            const InstRec* st = sm.recs[s];
+            const StageRec* st = sm.recs[s];
             for (int r0 = ((cnt - 1) >> 5) << 5; r0 >= 0; r0 -= 32) {
                 const int j = r0 + lane;
                 bool rel = false;
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(BB_THREADS, AUX ? 3 : 4) blend_bwd_kernel(cons
                 while (m) {
                     const int k = 31 - __clz(m);
                     m &= ~(1u << k);
-                    const InstRec* g = st + (r0 + k);
+                    const StageRec* g = st + (r0 + k);
                     const unsigned int pos = (unsigned)(lo + r0 + k);   // "contributor" index
                     const float4 q0 = g->q0;
                     const float4 q1 = g->q1;
@@ -281,8 +281,8 @@ __global__ void __launch_bounds__(BB_THREADS, AUX ? 3 : 4) blend_bwd_kernel(cons
         if (threadIdx.x == 0 && issued < nb) {
             mbar_wait(&sm.empty[s], ph);
             const int nhi = n - issued * BB_BATCH, nlo = max(0, nhi - BB_BATCH);
-            mbar_expect_tx(&sm.full[s], (uint32_t)(nhi - nlo) * 64u);
-            bulk_g2s(&sm.recs[s][0], src + nlo, (uint32_t)(nhi - nlo) * 64u, &sm.full[s]);
+            mbar_expect_tx(&sm.full[s], (uint32_t)(nhi - nlo) * kStageRecBytes);
+            bulk_g2s(&sm.recs[s][0], src + nlo, (uint32_t)(nhi - nlo) * kStageRecBytes, &sm.full[s]);
             ++issued;
         }
     }
@@ -334,7 +334,7 @@ struct __align__(16) B2Warp {
 };
 template <int STAGES, bool ACOL_SMEM>
 struct __align__(128) B2Smem {
-    InstRec recs[STAGES][B2_BATCH];
+    StageRec recs[STAGES][B2_BATCH];
     B2Warp warp[B2_WARPS];
     float amom[8][32];      // A fragments of the moment tile (identical for every warp): [2 s + h][lane]
     float acol[ACOL_SMEM ? B2_WARPS : 1][8][32];   // A fragments of the colour tile (per warp) when not kept in registers
@@ -345,7 +345,7 @@ struct __align__(128) B2Smem {
 
 // The forward's exact evaluation of one (pixel, Gaussian) pair (forward.cu:578-590 as compiled; see
 // blend_fwd.cu): decides the pairs the polynomial of the v2 kernel cannot (rare, kept out of line).
-__device__ __noinline__ float2 exact_pair(const InstRec* g, float pxf, float pyf) {
+__device__ __noinline__ float2 exact_pair(const StageRec* g, float pxf, float pyf) {
     const float4 q0 = g->q0, q1 = g->q1;
     const float dx = fsub(q0.x, pxf), dy = fsub(q0.y, pyf);
     const float power = ffma(ffma(dx, fmul(dx, q1.x), fmul(dy, fmul(dy, q1.z))), -0.5f, -fmul(dy, fmul(dx, q1.y)));
@@ -402,14 +402,14 @@ __global__ void __launch_bounds__(B2_THREADS, ACOL_SMEM ? 4 : 3) blend_bwd2_kern
     __syncthreads();
     const int n = min(n_list, (int)sm.nmax);
     const int nb = (n + B2_BATCH - 1) / B2_BATCH;
-    const InstRec* src = p.recs + range.x;
+    const StageRec* src = p.recs + range.x;
 
     int issued = 0;
     if (threadIdx.x == 0) {
         for (; issued < nb && issued < B2_STAGES; ++issued) {
             const int hi = n - issued * B2_BATCH, lo = max(0, hi - B2_BATCH);
-            mbar_expect_tx(&sm.full[issued], (uint32_t)(hi - lo) * 64u);
-            bulk_g2s(&sm.recs[issued][0], src + lo, (uint32_t)(hi - lo) * 64u, &sm.full[issued]);
+            mbar_expect_tx(&sm.full[issued], (uint32_t)(hi - lo) * kStageRecBytes);
+            bulk_g2s(&sm.recs[issued][0], src + lo, (uint32_t)(hi - lo) * kStageRecBytes, &sm.full[issued]);
         }
     }
 
@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(B2_THREADS, ACOL_SMEM ? 4 : 3) blend_bwd2_kern
         const int hi = n - b * B2_BATCH, lo = max(0, hi - B2_BATCH), cnt = hi - lo;
         mbar_wait_backoff(&sm.full[s], ph);
         if ((unsigned)lo < wmax) {
-            const InstRec* st = sm.recs[s];
+            const StageRec* st = sm.recs[s];
             for (int r0 = ((cnt - 1) >> 5) << 5; r0 >= 0; r0 -= 32) {
                 const int j = r0 + lane;
                 bool rel = false;
@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(B2_THREADS, ACOL_SMEM ? 4 : 3) blend_bwd2_kern
                     const float4 s1 = ws.s1[i];
                     const float pw = fmaf(u, fmaf(s1.x, u, fmaf(s1.y, v, s0.y)), fmaf(v, fmaf(s1.z, v, s0.z), s0.x));
                     const unsigned int posbits = __float_as_uint(s1.w);
-                    const InstRec* rec = st + ((posbits & 0x7fffffffu) - (unsigned)lo);   // staged record of this slot
+                    const StageRec* rec = st + ((posbits & 0x7fffffffu) - (unsigned)lo);   // staged record of this slot
                     bool contrib = (posbits & 0x7fffffffu) < my_last;
                     float G_c = ex2_approx(pw);
                     float og = s0.w * G_c;
@@ -598,8 +598,8 @@ __global__ void __launch_bounds__(B2_THREADS, ACOL_SMEM ? 4 : 3) blend_bwd2_kern
         if (threadIdx.x == 0 && issued < nb) {
             mbar_wait(&sm.empty[s], ph);
             const int nhi = n - issued * B2_BATCH, nlo = max(0, nhi - B2_BATCH);
-            mbar_expect_tx(&sm.full[s], (uint32_t)(nhi - nlo) * 64u);
-            bulk_g2s(&sm.recs[s][0], src + nlo, (uint32_t)(nhi - nlo) * 64u, &sm.full[s]);
+            mbar_expect_tx(&sm.full[s], (uint32_t)(nhi - nlo) * kStageRecBytes);
+            bulk_g2s(&sm.recs[s][0], src + nlo, (uint32_t)(nhi - nlo) * kStageRecBytes, &sm.full[s]);
             ++issued;
         }
     }
@@ -618,13 +618,13 @@ bool blend_bwd_is_raw(const BlendBwdParams& p) {
 cudaError_t launch_blend_bwd(const BlendBwdParams& p, cudaStream_t stream) {
     dim3 grid(p.grid_x, p.grid_y, 1);
     if (blend_bwd_is_raw(p)) {
-        // two builds of the same kernel: colour fragments in shared memory + 4 stages (4 CTAs / SM, 64 registers)
+        // two builds of the same kernel: colour fragments in shared memory + 3 stages (4 CTAs / SM, 64 registers)
         // or in registers + 3 stages (3 CTAs / SM, 80 registers)
         static const bool regs_variant = getenv("FDGS_BWD2_REGS") != nullptr;
         static bool attr_set = false;
         if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(blend_bwd2_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)sizeof(B2Smem<4, true>));
+            cudaError_t e = cudaFuncSetAttribute(blend_bwd2_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)sizeof(B2Smem<3, true>));
             if (e == cudaSuccess)
                 e = cudaFuncSetAttribute(blend_bwd2_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(B2Smem<3, false>));
@@ -632,7 +632,7 @@ cudaError_t launch_blend_bwd(const BlendBwdParams& p, cudaStream_t stream) {
             attr_set = true;
         }
         if (regs_variant) blend_bwd2_kernel<3, false><<<grid, B2_THREADS, sizeof(B2Smem<3, false>), stream>>>(p);
-        else blend_bwd2_kernel<4, true><<<grid, B2_THREADS, sizeof(B2Smem<4, true>), stream>>>(p);
+        else blend_bwd2_kernel<3, true><<<grid, B2_THREADS, sizeof(B2Smem<3, true>), stream>>>(p);
     } else if (!p.dL_depths && !p.dL_masks && !p.dL_dpix_flow) {
         blend_bwd_kernel<false><<<grid, BB_THREADS, 0, stream>>>(p);
     } else {

@@ -26,7 +26,7 @@ constexpr int BF_BATCH = 128;
 constexpr int BF_STAGES = 3;
 
 struct __align__(128) BlendFwdSmem {
-    InstRec recs[BF_STAGES][BF_BATCH];
+    StageRec recs[BF_STAGES][BF_BATCH];
     uint64_t full[BF_STAGES];
     uint64_t empty[BF_STAGES];
     int done_warps;
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(BF_THREADS) blend_fwd_kernel(const BlendFwdPar
     const uint2 range = p.ranges[tile];
     const int n = (int)(range.y - range.x);
     const int nb = (n + BF_BATCH - 1) / BF_BATCH;
-    const InstRec* src = p.recs + range.x;
+    const StageRec* src = p.recs + range.x;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < BF_STAGES; ++s) {
@@ -63,8 +63,8 @@ __global__ void __launch_bounds__(BF_THREADS) blend_fwd_kernel(const BlendFwdPar
     if (threadIdx.x == 0) {
         for (; issued < nb && issued < BF_STAGES; ++issued) {
             const int cnt = min(BF_BATCH, n - issued * BF_BATCH);
-            mbar_expect_tx(&sm.full[issued], (uint32_t)cnt * 64u);
-            bulk_g2s(&sm.recs[issued][0], src + (size_t)issued * BF_BATCH, (uint32_t)cnt * 64u, &sm.full[issued]);
+            mbar_expect_tx(&sm.full[issued], (uint32_t)cnt * kStageRecBytes);
+            bulk_g2s(&sm.recs[issued][0], src + (size_t)issued * BF_BATCH, (uint32_t)cnt * kStageRecBytes, &sm.full[issued]);
         }
     }
 
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(BF_THREADS) blend_fwd_kernel(const BlendFwdPar
         mbar_wait(&sm.full[s], ph);   // already complete: gives every lane the acquire on the batch
         if (!warp_done) {
             const int cnt = min(BF_BATCH, n - b * BF_BATCH);
-            const InstRec* st = sm.recs[s];
+            const StageRec* st = sm.recs[s];
             for (int r0 = 0; r0 < cnt; r0 += 32) {
                 const int j = r0 + lane;
                 bool rel = false;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(BF_THREADS) blend_fwd_kernel(const BlendFwdPar
                 while (m) {
                     const int k = __ffs(m) - 1;
                     m &= m - 1;
-                    const InstRec* g = st + (r0 + k);
+                    const StageRec* g = st + (r0 + k);
                     const float4 q0 = g->q0;   // x, y, pmin, -
                     const float4 q1 = g->q1;   // A, B, C, opacity
                     // reference: forward.cu:578-581 (contraction as compiled)
@@ -151,8 +151,8 @@ __global__ void __launch_bounds__(BF_THREADS) blend_fwd_kernel(const BlendFwdPar
             }
             if (go) {
                 const int cnt = min(BF_BATCH, n - issued * BF_BATCH);
-                mbar_expect_tx(&sm.full[s], (uint32_t)cnt * 64u);
-                bulk_g2s(&sm.recs[s][0], src + (size_t)issued * BF_BATCH, (uint32_t)cnt * 64u, &sm.full[s]);
+                mbar_expect_tx(&sm.full[s], (uint32_t)cnt * kStageRecBytes);
+                bulk_g2s(&sm.recs[s][0], src + (size_t)issued * BF_BATCH, (uint32_t)cnt * kStageRecBytes, &sm.full[s]);
                 ++issued;
             }
         }

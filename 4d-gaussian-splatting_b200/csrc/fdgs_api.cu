@@ -141,7 +141,7 @@ struct ImageState {
 };
 
 struct BinningState {
-    fdgs::InstRec* recs;     // [R] instance records in tile-sorted order
+    fdgs::StageRec* recs;    // [R] instance records in tile-sorted order (80-byte stride, see fdgs_common.cuh)
     uint32_t* point_list;    // [R] sorted Gaussian indices (the reference's point_list)
     uint64_t* keys;          // [R] depth_bits<<32 | index, grouped by tile
     size_t bytes;
@@ -149,7 +149,7 @@ struct BinningState {
         BinningState b;
         Carver c(base);
         const size_t r = (size_t)(R > 0 ? R : 0);
-        b.recs = c.take<fdgs::InstRec>(r);
+        b.recs = c.take<fdgs::StageRec>(r);
         b.point_list = c.take<uint32_t>(r);
         b.keys = c.take<uint64_t>(r);
         b.bytes = c.total();

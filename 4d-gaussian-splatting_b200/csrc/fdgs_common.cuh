@@ -249,6 +249,18 @@ struct __align__(16) InstRec {
 };
 static_assert(sizeof(InstRec) == 64, "InstRec must be 64 bytes");
 
+// The same record as it is stored in the tile-sorted instance stream (`recs`) and staged in shared memory by the
+// blend kernels: padded to 80 bytes.  With a 64-byte stride the culling loads -- lane j reads plane q of record j,
+// LDS.128 at address 64 j + 16 q -- hit only two 4-bank groups (4-way conflict, 16 wavefronts per load, measured
+// 61 M of the ~110-190 M shared-memory wavefronts of each blend kernel); with an 80-byte stride 8 consecutive
+// records cover all 32 banks (20 j mod 32 = 0, 20, 8, 28, 16, 4, 24, 12) and the loads are conflict-free.  The
+// extra 16 bytes per instance are HBM traffic the blend kernels, at < 8 % of DRAM bandwidth, do not feel.
+struct __align__(16) StageRec {
+    float4 q0, q1, q2, q3, pad;
+};
+static_assert(sizeof(StageRec) == 80, "StageRec must be 80 bytes");
+constexpr uint32_t kStageRecBytes = 80u;
+
 // Can the instance (centre x0,y0; conic A,B,C; pmin; slopes sbc=-B/C, sba=-B/A) contribute to any
 // pixel of the rectangle [bx0,bx1] x [by0,by1]?  It contributes at offset d only if
 // q(d) = 0.5*(A dx^2 + C dy^2) + B dx dy <= -pmin.  q is convex, so its minimum over the rectangle is

@@ -58,7 +58,7 @@ cudaError_t launch_bin_scatter(int P, const uint4* binrec, int grid_x, int grid_
 // sorts every tile's keys and writes the 64-byte instance records + the sorted index list
 int tile_sort_pack_kernel_count(int max_count);
 cudaError_t launch_tile_sort_pack(int num_tiles, int max_count, int R, const uint2* ranges, uint64_t* keys,
-                                  const InstRec* grec, InstRec* recs, uint32_t* point_list, cudaStream_t stream);
+                                  const InstRec* grec, StageRec* recs, uint32_t* point_list, cudaStream_t stream);
 cudaError_t launch_unpack_grec(int P, const InstRec* grec, const int* radii, float* depths, float* means2D,
                                float* conic_opacity, float* rgb, cudaStream_t stream);
 
@@ -66,7 +66,7 @@ cudaError_t launch_unpack_grec(int P, const InstRec* grec, const int* radii, flo
 struct BlendFwdParams {
     int W, H, grid_x, grid_y;
     const uint2* ranges;
-    const InstRec* recs;
+    const StageRec* recs;
     const float* background;
     float* final_T;        // [H*W]  (scratch copy used by the backward)
     uint32_t* n_contrib;   // [H*W]
@@ -80,7 +80,7 @@ cudaError_t launch_blend_fwd(const BlendFwdParams& p, cudaStream_t stream);
 struct BlendBwdParams {
     int W, H, grid_x, grid_y;
     const uint2* ranges;
-    const InstRec* recs;
+    const StageRec* recs;
     const float* background;
     const float* final_T;
     const uint32_t* n_contrib;
