@@ -301,8 +301,9 @@ __global__ void __launch_bounds__(BB_THREADS, AUX ? 3 : 4) blend_bwd_kernel(cons
 //     log2 e) and parks them in a per-warp shared-memory slot; a step is then 2 LDS.128 + 5 FFMA +
 //     1 MUFU.EX2 instead of bit-scan + 2 LDS.128 + 2 FADD + 7 FMUL/FFMA + FMUL + MUFU.  The polynomial
 //     differs from the forward's exact power by a few 1e-6 (absolute); pairs whose alpha lands within
-//     2e-7 of the 1/255 cut, or whose power is within 1e-4 of 0, are re-decided with the forward's
-//     exact arithmetic from the staged record, so both passes agree on the set of contributors.
+//     6e-7 of the 1/255 cut, or whose power is within 1e-4 of 0, and every pair of an instance whose
+//     quadratic has large cancelling terms (thin rotated Gaussians far from their centre), are re-decided
+//     with the forward's exact arithmetic from the staged record, so both passes agree on the contributors.
 //   * every per-Gaussian gradient is a weighted sum over the warp's 32 pixels with weights that do not
 //     depend on the Gaussian: the pixel's colour gradient (3) for  a1 = alpha*T, and the monomials
 //     1, u, v, u^2, uv, v^2 of the pixel offset for  w = G * dL/dalpha.  So the reduction is a matrix
@@ -618,21 +619,16 @@ bool blend_bwd_is_raw(const BlendBwdParams& p) {
 cudaError_t launch_blend_bwd(const BlendBwdParams& p, cudaStream_t stream) {
     dim3 grid(p.grid_x, p.grid_y, 1);
     if (blend_bwd_is_raw(p)) {
-        // two builds of the same kernel: colour fragments in shared memory + 3 stages (4 CTAs / SM, 64 registers)
-        // or in registers + 3 stages (3 CTAs / SM, 80 registers)
-        static const bool regs_variant = getenv("FDGS_BWD2_REGS") != nullptr;
+        // colour fragments in shared memory + 3 stages: 64 registers, 53 KB -> 4 CTAs / SM.  (Keeping them in
+        // registers costs 80 registers -> 3 CTAs / SM and measured 8 % slower.)
         static bool attr_set = false;
         if (!attr_set) {
             cudaError_t e = cudaFuncSetAttribute(blend_bwd2_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)sizeof(B2Smem<3, true>));
-            if (e == cudaSuccess)
-                e = cudaFuncSetAttribute(blend_bwd2_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(B2Smem<3, false>));
             if (e != cudaSuccess) return e;
             attr_set = true;
         }
-        if (regs_variant) blend_bwd2_kernel<3, false><<<grid, B2_THREADS, sizeof(B2Smem<3, false>), stream>>>(p);
-        else blend_bwd2_kernel<3, true><<<grid, B2_THREADS, sizeof(B2Smem<3, true>), stream>>>(p);
+        blend_bwd2_kernel<3, true><<<grid, B2_THREADS, sizeof(B2Smem<3, true>), stream>>>(p);
     } else if (!p.dL_depths && !p.dL_masks && !p.dL_dpix_flow) {
         blend_bwd_kernel<false><<<grid, BB_THREADS, 0, stream>>>(p);
     } else {

@@ -33,3 +33,10 @@ if has full; then
       -f -o $OUT/${TAG}_blend python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_full.log 2>&1
   ls -la $OUT/${TAG}_blend.ncu-rep
 fi
+if has sanitize; then
+  # memcheck of the small golden cases through the whole fwd+bwd path (both backward kernels)
+  timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests -m gpu -x -q \
+      -k "golden and (tiny or ragged or negfov) or colour_only_backward_equals_zero_aux_gradients and small" > $OUT/${TAG}_memcheck.log 2>&1
+  echo "memcheck exit $?" >> $OUT/${TAG}_memcheck.log
+  grep -E "ERROR SUMMARY|passed|failed|memcheck exit" $OUT/${TAG}_memcheck.log | tail -5
+fi
