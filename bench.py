@@ -384,7 +384,7 @@ def main():
             pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "algorithmic_bytes": alg, "peak_source": peak_src,
-                    "note": "dominant kernel is instruction-issue / shared-memory bound, not HBM bound (profiles/r01_blend_ncu_v8.md)",
+                    "note": "dominant kernel is instruction-issue / shared-memory bound, not HBM bound (profiles/r01_blend_ncu_v11.md)",
                     "frame": {"algorithmic_bytes": b_fwd + b_bwd, "achieved": (b_fwd + b_bwd) / (ms_step * 1e-3) / 1e9,
                               "frac": (b_fwd + b_bwd) / (ms_step * 1e-3) / 1e9 / peak}}
 
