@@ -9,7 +9,8 @@ view of the synthetic scene of SURVEY.md section 8(d), through the reference-fac
   value   inputs resident in HBM, CUDA events, K steps after W warm-ups, max over ranks
   e2e     same call with HOST buffers: per step the camera matrices and the upstream gradient image
           are copied host->device from pinned memory (the image on a copy stream, overlapping the
-          forward, both arms alike) and the loss is read back device->host
+          forward, both arms alike) and the loss is read back device->host (asynchronously into pinned
+          memory, collected one step later and before the clock stops, so the launch queue never drains)
   N > 1   one view per rank (weak scaling), replicated Gaussians, SUM all-reduce (NCCL) of the
           per-Gaussian parameter gradients (rows of the union of the ranks' rendered Gaussians, one flat
           buffer) + the densification statistics inside the step
@@ -147,6 +148,9 @@ class Runner:
             self.ref_api = ref_api
         self.G_dev = wl.G_host.to(wl.device)
         self.copy_stream = torch.cuda.Stream(device=wl.device)
+        self.loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self.loss_ready = torch.cuda.Event()
+        self.pending = False
         self.last = None
 
     def _raster(self, settings):
@@ -192,7 +196,22 @@ class Runner:
         loss = (color * G).sum()
         loss.backward()
         self.last = (loss, radii, means2D)
-        return float(loss.item())
+        # device->host read of the step's result: an asynchronous copy into pinned memory, collected at the start
+        # of the next step (and by drain() before the clock stops) -- the way a training loop logs its loss
+        # without stalling the launch queue.  Every step's result is read inside the timed region.
+        prev = self.drain()
+        self.loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        self.loss_ready.record(cur)
+        self.pending = True
+        return prev
+
+    def drain(self):
+        """Wait for and return the most recent step's loss (None if nothing is pending)."""
+        if not getattr(self, "pending", False):
+            return None
+        self.loss_ready.synchronize()
+        self.pending = False
+        return float(self.loss_host[0])
 
     def h2d_bytes(self):
         return int(self.wl.G_host.numel() * 4 + sum(h.numel() * 4 for h in self.wl.cam_host.values()))
@@ -201,9 +220,11 @@ class Runner:
         return [v.grad for v in self.wl.params.values()]
 
 
-def timed(fn, steps, warmup, device, world):
+def timed(fn, steps, warmup, device, world, finish=None):
     for _ in range(warmup):
         fn()
+    if finish is not None:
+        finish()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(device)
@@ -212,6 +233,8 @@ def timed(fn, steps, warmup, device, world):
     e0.record()
     for _ in range(steps):
         fn()
+    if finish is not None:
+        finish()      # e.g. collect the last step's host read-back before the clock stops
     e1.record()
     torch.cuda.synchronize(device)
     wall = time.perf_counter() - t0
@@ -339,7 +362,7 @@ def main():
     value = eff_world * mpix / (ms_step * 1e-3)
 
     # ---- e2e: host buffers ---------------------------------------------------------------------------
-    ms_e2e, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2), device, eff_world)
+    ms_e2e, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2), device, eff_world, finish=runner.drain)
     e2e = {"value": eff_world * mpix / (ms_e2e * 1e-3), "unit": "Mpixels/s", "ms_per_step": ms_e2e,
            "h2d_bytes_per_step": runner.h2d_bytes(), "d2h_bytes_per_step": 4}
 
