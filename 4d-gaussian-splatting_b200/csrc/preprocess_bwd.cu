@@ -30,7 +30,7 @@ namespace fdgs {
 namespace {
 
 constexpr int SB_THREADS = 128;   // SH kernel: Gaussians per CTA
-constexpr int SB_CAP = 64;        // shared-memory row slots per CTA (rendered rows per round)
+constexpr int SB_CAP = 48;        // shared-memory row slots per CTA (rendered rows per round)
 constexpr int GB_THREADS = 128;   // geometry kernel
 
 __device__ __forceinline__ float3 dnormvdv3(float3 v, float3 dv) {   // auxiliary.h:108-118
@@ -90,7 +90,8 @@ __device__ __forceinline__ void sh_basis_deriv(float x, float y, float z, int de
 
 // per-Gaussian constants of the SH backward
 struct ShCtx {
-    ShDeriv SD;
+    float3 dirn;           // unit view direction; the basis / derivative table is rebuilt from it where needed
+    int deg;
     float dRGB[3];
     float3 dir_orig;
     float tw[3], dtw[3];   // temporal weight / its (reference-style) derivative per 16-coefficient block
@@ -108,7 +109,8 @@ __device__ __forceinline__ void sh_ctx_init(const PreprocessBwdParams& a, int id
     const float mx = a.means3D[3 * idx + 0], my = a.means3D[3 * idx + 1], mz = a.means3D[3 * idx + 2];
     c.dir_orig = make_float3(mx - a.campos[0], my - a.campos[1], mz - a.campos[2]);
     const float len = sqrtf(c.dir_orig.x * c.dir_orig.x + c.dir_orig.y * c.dir_orig.y + c.dir_orig.z * c.dir_orig.z);
-    sh_basis_deriv(c.dir_orig.x / len, c.dir_orig.y / len, c.dir_orig.z / len, a.D, c.SD);
+    c.dirn = make_float3(c.dir_orig.x / len, c.dir_orig.y / len, c.dir_orig.z / len);
+    c.deg = a.D;
     c.ncoef = (a.D + 1) * (a.D + 1);
     c.tw[0] = 1.f; c.tw[1] = c.tw[2] = 0.f;
     c.dtw[0] = c.dtw[1] = c.dtw[2] = 0.f;
@@ -132,25 +134,31 @@ __device__ __forceinline__ void sh_ctx_init(const PreprocessBwdParams& a, int id
 // Returns the direction sums and the temporal term.  NQ = number of float4 in the row (3*M/4).
 __device__ __forceinline__ void sh_row_inplace(float4* rowq, int nq, const ShCtx& c, float& ddx, float& ddy,
                                                float& ddz, float& dtt) {
-    ddx = ddy = ddz = dtt = 0.f;
     const int ngroups = nq / 3;   // groups of 4 coefficients
+    // Coefficient group (4 k .. 4 k + 3) outermost, the (up to) three 16-coefficient blocks inside: the basis
+    // values / derivatives are evaluated per group (sh_basis_deriv is fully inlined and everything but the four
+    // entries of the group is dead code), so the 64-entry table never occupies registers -- the kernel goes from
+    // 127 to ~80 registers and from 4 to 6 CTAs per SM.  Per block the sums still run over k in ascending order.
+    float sx[3] = {0.f, 0.f, 0.f}, sy[3] = {0.f, 0.f, 0.f}, sz[3] = {0.f, 0.f, 0.f}, sl[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int blk = 0; blk < 3; ++blk) {
-        if (blk * 4 >= ngroups) break;
-        const bool blk_on = blk < c.nblk;
-        float sx = 0.f, sy = 0.f, sz = 0.f, sl = 0.f;
+    for (int kg = 0; kg < 4; ++kg) {
+        // opaque copies: keep the compiler from hoisting one shared 64-entry table out of the group loop
+        float gx = c.dirn.x, gy = c.dirn.y, gz = c.dirn.z;
+        asm volatile("" : "+f"(gx), "+f"(gy), "+f"(gz));
+        ShDeriv S;
+        sh_basis_deriv(gx, gy, gz, c.deg, S);
+        const float l0 = S.l[0];
 #pragma unroll
-        for (int kg = 0; kg < 4; ++kg) {
+        for (int blk = 0; blk < 3; ++blk) {
             const int G = blk * 4 + kg;
-            if (G >= ngroups) break;
-            float4 q[3];
+            if (G >= ngroups) continue;
+            const bool grp_on = (blk < c.nblk) && (kg * 4 < c.ncoef);
             float f[12];
-            const bool grp_on = blk_on && (kg * 4 < c.ncoef);
             if (grp_on) {
-                q[0] = rowq[3 * G + 0]; q[1] = rowq[3 * G + 1]; q[2] = rowq[3 * G + 2];
-                f[0] = q[0].x; f[1] = q[0].y; f[2] = q[0].z; f[3] = q[0].w;
-                f[4] = q[1].x; f[5] = q[1].y; f[6] = q[1].z; f[7] = q[1].w;
-                f[8] = q[2].x; f[9] = q[2].y; f[10] = q[2].z; f[11] = q[2].w;
+                const float4 q0 = rowq[3 * G + 0], q1 = rowq[3 * G + 1], q2 = rowq[3 * G + 2];
+                f[0] = q0.x; f[1] = q0.y; f[2] = q0.z; f[3] = q0.w;
+                f[4] = q1.x; f[5] = q1.y; f[6] = q1.z; f[7] = q1.w;
+                f[8] = q2.x; f[9] = q2.y; f[10] = q2.z; f[11] = q2.w;
             }
             float o[12];
 #pragma unroll
@@ -159,12 +167,12 @@ __device__ __forceinline__ void sh_row_inplace(float4* rowq, int nq, const ShCtx
                 float w = 0.f;
                 if (grp_on && k < c.ncoef) {
                     const float sk = f[3 * j] * c.dRGB[0] + f[3 * j + 1] * c.dRGB[1] + f[3 * j + 2] * c.dRGB[2];
-                    sx += c.SD.dx[k] * sk;
-                    sy += c.SD.dy[k] * sk;
-                    sz += c.SD.dz[k] * sk;
-                    sl += c.SD.l[k] * sk;
+                    sx[blk] += S.dx[k] * sk;
+                    sy[blk] += S.dy[k] * sk;
+                    sz[blk] += S.dz[k] * sk;
+                    sl[blk] += S.l[k] * sk;
                     // dL_dsh[1] = l0m0 * dL_dRGB in the 4D variant (quirk, backward.cu:190)
-                    w = (blk == 0) ? ((c.sh4d && k == 1) ? c.SD.l[0] : c.SD.l[k]) : c.tw[blk] * c.SD.l[k];
+                    w = (blk == 0) ? ((c.sh4d && k == 1) ? l0 : S.l[k]) : c.tw[blk] * S.l[k];
                 }
                 o[3 * j + 0] = w * c.dRGB[0];
                 o[3 * j + 1] = w * c.dRGB[1];
@@ -174,11 +182,15 @@ __device__ __forceinline__ void sh_row_inplace(float4* rowq, int nq, const ShCtx
             rowq[3 * G + 1] = make_float4(o[4], o[5], o[6], o[7]);
             rowq[3 * G + 2] = make_float4(o[8], o[9], o[10], o[11]);
         }
-        if (blk_on) {
-            ddx += c.tw[blk] * sx;
-            ddy += c.tw[blk] * sy;
-            ddz += c.tw[blk] * sz;
-            if (blk > 0) dtt = c.dtw[blk] * sl;   // overwrites: backward.cu:403
+    }
+    ddx = ddy = ddz = dtt = 0.f;
+#pragma unroll
+    for (int blk = 0; blk < 3; ++blk) {
+        if (blk * 4 < ngroups && blk < c.nblk) {
+            ddx += c.tw[blk] * sx[blk];
+            ddy += c.tw[blk] * sy[blk];
+            ddz += c.tw[blk] * sz[blk];
+            if (blk > 0) dtt = c.dtw[blk] * sl[blk];   // overwrites: backward.cu:403
         }
     }
     // coefficients beyond the three 16-blocks (M > 48) are never used: zero gradient
@@ -187,7 +199,7 @@ __device__ __forceinline__ void sh_row_inplace(float4* rowq, int nq, const ShCtx
 
 // ---- SH backward ----------------------------------------------------------------------------------
 template <bool BULK>
-__global__ void __launch_bounds__(SB_THREADS, 4) sh_bwd_kernel(const PreprocessBwdParams a) {
+__global__ void __launch_bounds__(SB_THREADS, 6) sh_bwd_kernel(const PreprocessBwdParams a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ short slot_of[SB_THREADS];   // rank among the rendered rows of this CTA, -1 = not rendered
@@ -273,6 +285,8 @@ __global__ void __launch_bounds__(SB_THREADS, 4) sh_bwd_kernel(const PreprocessB
         const float* grow = a.shs + (size_t)idx * row_floats;
         float* drow = a.dL_dsh + (size_t)idx * row_floats;
         float ddx = 0.f, ddy = 0.f, ddz = 0.f, dtt = 0.f;
+        ShDeriv SDg;
+        sh_basis_deriv(c.dirn.x, c.dirn.y, c.dirn.z, c.deg, SDg);
         for (int blk = 0; blk * 16 < a.M; ++blk) {
             float sx = 0.f, sy = 0.f, sz = 0.f, sl = 0.f;
             const bool blk_on = blk < c.nblk;
@@ -282,8 +296,8 @@ __global__ void __launch_bounds__(SB_THREADS, 4) sh_bwd_kernel(const PreprocessB
                 if (blk_on && k < c.ncoef) {
                     const float sk = __ldg(grow + 3 * cidx) * c.dRGB[0] + __ldg(grow + 3 * cidx + 1) * c.dRGB[1] +
                                      __ldg(grow + 3 * cidx + 2) * c.dRGB[2];
-                    sx += c.SD.dx[k] * sk; sy += c.SD.dy[k] * sk; sz += c.SD.dz[k] * sk; sl += c.SD.l[k] * sk;
-                    w = (blk == 0) ? ((c.sh4d && k == 1) ? c.SD.l[0] : c.SD.l[k]) : c.tw[blk < 3 ? blk : 0] * c.SD.l[k];
+                    sx += SDg.dx[k] * sk; sy += SDg.dy[k] * sk; sz += SDg.dz[k] * sk; sl += SDg.l[k] * sk;
+                    w = (blk == 0) ? ((c.sh4d && k == 1) ? SDg.l[0] : SDg.l[k]) : c.tw[blk < 3 ? blk : 0] * SDg.l[k];
                 }
                 drow[3 * cidx + 0] = w * c.dRGB[0];
                 drow[3 * cidx + 1] = w * c.dRGB[1];
