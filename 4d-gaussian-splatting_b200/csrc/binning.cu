@@ -43,6 +43,7 @@ namespace {
 
 constexpr int BIN_CTAS = 148;      // one persistent CTA per SM; also the row count of the count matrix
 constexpr int BIN_THREADS = 1024;
+constexpr int BIN_SMALL = 8;       // rectangles of up to this many tiles are binned by their own lane
 constexpr int SCAN_THREADS = 1024;
 constexpr size_t BIN_SMEM_LIMIT = 200 * 1024;
 
@@ -78,19 +79,31 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_pass_kernel(int P, int chunk,
         nxt = (gn < end) ? binrec[gn] : none;
         // x = x0 | y0 << 16, y = x1 | y1 << 16 (tile coordinates), z = depth bits
         const int x0 = (int)(br.x & 0xffffu), y0 = (int)(br.x >> 16), x1 = (int)(br.y & 0xffffu), y1 = (int)(br.y >> 16);
-        const bool vis = (x1 > x0) && (y1 > y0);
-        uint32_t mask = __ballot_sync(0xffffffffu, vis);
+        const int w = x1 - x0;
+        const int n = ((x1 > x0) && (y1 > y0)) ? w * (y1 - y0) : 0;
+        // Small rectangles (the common case: a ~1.5-pixel-sigma Gaussian touches 1-4 tiles) are walked by their own
+        // lane -- no shuffles, no division, the warp runs for max(n) <= BIN_SMALL iterations; only the large ones
+        // are spread over the 32 lanes.  The order inside a tile's segment is arbitrary either way (sorted later).
+        if (n > 0 && n <= BIN_SMALL) {
+            const uint64_t key = SCATTER ? (((uint64_t)br.z << 32) | (uint32_t)(g0 + lane)) : 0ull;
+            for (int ty = y0; ty < y1; ++ty) {
+                for (int tx = x0; tx < x1; ++tx) {
+                    const uint32_t slot = atomicAdd(&hist[ty * grid_x + tx], 1u);
+                    if (SCATTER) keys[slot] = key;
+                }
+            }
+        }
+        uint32_t mask = __ballot_sync(0xffffffffu, n > BIN_SMALL);
         while (mask) {
             const int src = __ffs(mask) - 1;
             mask &= mask - 1;
             const int bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
-            const int bx1 = __shfl_sync(0xffffffffu, x1, src), by1 = __shfl_sync(0xffffffffu, y1, src);
-            const int w = bx1 - bx0, n = w * (by1 - by0);
+            const int bw = __shfl_sync(0xffffffffu, w, src), bn = __shfl_sync(0xffffffffu, n, src);
             uint64_t key = 0;
             // key: depth bits (positive floats: integer order == float order) then Gaussian index
             if (SCATTER) key = ((uint64_t)__shfl_sync(0xffffffffu, br.z, src) << 32) | (uint32_t)(g0 + src);
-            for (int i = lane; i < n; i += 32) {
-                const int ry = i / w, rx = i - ry * w;
+            for (int i = lane; i < bn; i += 32) {
+                const int ry = i / bw, rx = i - ry * bw;
                 const int t = (by0 + ry) * grid_x + bx0 + rx;
                 const uint32_t slot = atomicAdd(&hist[t], 1u);
                 if (SCATTER) keys[slot] = key;
