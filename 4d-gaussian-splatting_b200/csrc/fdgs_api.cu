@@ -219,6 +219,8 @@ int fdgs_forward(const fdgs_forward_args* a, fdgs_alloc_fn geom_alloc, void* geo
         }
     }
     const int grid_x = (W + fdgs::TILE_X - 1) / fdgs::TILE_X, grid_y = (H + fdgs::TILE_Y - 1) / fdgs::TILE_Y;
+    // tile coordinates travel as 16-bit fields of the per-Gaussian bin record (preprocess_fwd.cu / binning.cu)
+    if (grid_x > 65535 || grid_y > 65535) return fail(FDGS_ERR_UNSUPPORTED, "image larger than 1048560 pixels on a side");
     const size_t N = (size_t)W * H;
 
     // scratch: geometry + image
