@@ -41,7 +41,9 @@
 namespace fdgs {
 namespace {
 
-constexpr int BIN_CTAS = 148;      // one persistent CTA per SM; also the row count of the count matrix
+constexpr int BIN_CTAS_MAX = 192;  // upper bound of the row count of the count matrix (register array in column_scan)
+// one persistent CTA per SM of the current device (148 on a B200); also the row count of the count matrix
+inline int bin_cta_count() { return min(device_sm_count(), BIN_CTAS_MAX); }
 constexpr int BIN_THREADS = 1024;
 constexpr int BIN_SMALL = 8;       // rectangles of up to this many tiles are binned by their own lane
 constexpr int SCAN_THREADS = 1024;
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_pass_kernel(int P, int chunk,
 // 32 tiles x 8 row groups per CTA: every thread owns <= ceil(rows / 8) consecutive rows of one tile column
 // (kept in registers), the groups' partial sums are combined through shared memory.  Coalesced along tiles.
 constexpr int CS_GROUPS = 8;
-constexpr int CS_MAXROWS = (BIN_CTAS + CS_GROUPS - 1) / CS_GROUPS;
+constexpr int CS_MAXROWS = (BIN_CTAS_MAX + CS_GROUPS - 1) / CS_GROUPS;
 __global__ void __launch_bounds__(256) column_scan_kernel(int num_tiles, int rows, uint32_t* __restrict__ matrix,
                                                           uint32_t* __restrict__ tile_total) {
     __shared__ uint32_t part[CS_GROUPS][32];
@@ -161,8 +163,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int num_tiles, 
     __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
     __shared__ uint32_t carry;
     __shared__ uint32_t max_count;
+    __shared__ unsigned long long total64;   // the true instance total: detects a wrap of the 32-bit offsets
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { carry = 0; max_count = 0; }
+    if (tid == 0) { carry = 0; max_count = 0; total64 = 0ull; }
     __syncthreads();
     uint32_t my_max = 0;
     for (int base = 0; base < num_tiles; base += SCAN_THREADS) {
@@ -194,12 +197,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(int num_tiles, 
             ranges[t] = c ? make_uint2(before, before + c) : make_uint2(0u, 0u);
         }
         __syncthreads();
-        if (tid == SCAN_THREADS - 1) carry = before + c;
+        if (tid == SCAN_THREADS - 1) {
+            total64 += (unsigned long long)warp_sums[SCAN_THREADS / 32 - 1];
+            carry = before + c;
+        }
         __syncthreads();
     }
     atomicMax(&max_count, my_max);
     __syncthreads();
-    if (tid == 0) { info[0] = carry; info[1] = max_count; }
+    // info[2] != 0: more than 2^31 - 1 instances -- the 32-bit offsets / the int num_rendered of the API cannot hold it
+    if (tid == 0) { info[0] = carry; info[1] = max_count; info[2] = (total64 > 0x7fffffffull) ? 1u : 0u; info[3] = 0u; }
 }
 
 // ---- 4. per-tile sort ------------------------------------------------------------------------------------
@@ -411,41 +418,52 @@ __global__ void unpack_grec_kernel(int P, const InstRec* __restrict__ grec, cons
 
 }  // namespace
 
-int bin_ctas() { return BIN_CTAS; }
+int device_sm_count() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev >= 0 && dev < 64) {
+        const int c = cache[dev].load(std::memory_order_relaxed);
+        if (c > 0) return c;
+    }
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (dev >= 0 && dev < 64) cache[dev].store(n, std::memory_order_relaxed);
+    return n;
+}
+
+int bin_ctas() { return bin_cta_count(); }
 
 template <bool SCATTER>
 static cudaError_t launch_bin_pass(int P, const uint4* binrec, int grid_x, int grid_y,
                                    uint32_t* matrix, const uint32_t* tile_offset, uint64_t* keys, cudaStream_t stream) {
     if (P <= 0) return cudaSuccess;
     const int num_tiles = grid_x * grid_y;
-    int chunk = (P + BIN_CTAS - 1) / BIN_CTAS;
+    const int ctas = bin_cta_count();
+    int chunk = (P + ctas - 1) / ctas;
     chunk = (chunk + 31) & ~31;
     const size_t smem = (size_t)num_tiles * sizeof(uint32_t);
     if (smem <= BIN_SMEM_LIMIT) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(bin_pass_kernel<SCATTER, true>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIN_SMEM_LIMIT);
-            if (e != cudaSuccess) return e;
-            attr_set = true;
-        }
-        bin_pass_kernel<SCATTER, true><<<BIN_CTAS, BIN_THREADS, smem, stream>>>(P, chunk, binrec, grid_x, num_tiles, matrix,
-                                                                                tile_offset, keys);
+        static PerDeviceOnce once;
+        cudaError_t e = ensure_dynamic_smem(bin_pass_kernel<SCATTER, true>, (int)BIN_SMEM_LIMIT, once);
+        if (e != cudaSuccess) return e;
+        bin_pass_kernel<SCATTER, true><<<ctas, BIN_THREADS, smem, stream>>>(P, chunk, binrec, grid_x, num_tiles, matrix,
+                                                                            tile_offset, keys);
     } else {
-        bin_pass_kernel<SCATTER, false><<<BIN_CTAS, BIN_THREADS, 0, stream>>>(P, chunk, binrec, grid_x, num_tiles, matrix,
-                                                                              tile_offset, keys);
+        bin_pass_kernel<SCATTER, false><<<ctas, BIN_THREADS, 0, stream>>>(P, chunk, binrec, grid_x, num_tiles, matrix,
+                                                                          tile_offset, keys);
     }
     return cudaGetLastError();
 }
 
 cudaError_t launch_bin_count(int P, const uint4* binrec, int grid_x, int grid_y, uint32_t* matrix, cudaStream_t stream) {
-    if (P <= 0) return cudaMemsetAsync(matrix, 0, (size_t)BIN_CTAS * grid_x * grid_y * sizeof(uint32_t), stream);
+    if (P <= 0) return cudaMemsetAsync(matrix, 0, (size_t)bin_cta_count() * grid_x * grid_y * sizeof(uint32_t), stream);
     return launch_bin_pass<false>(P, binrec, grid_x, grid_y, matrix, nullptr, nullptr, stream);
 }
 
 cudaError_t launch_tile_scan(int num_tiles, uint32_t* matrix, uint32_t* tile_total, uint32_t* tile_offset, uint2* ranges,
                              uint32_t* info, cudaStream_t stream) {
-    column_scan_kernel<<<(num_tiles + 31) / 32, 256, 0, stream>>>(num_tiles, BIN_CTAS, matrix, tile_total);
+    column_scan_kernel<<<(num_tiles + 31) / 32, 256, 0, stream>>>(num_tiles, bin_cta_count(), matrix, tile_total);
     tile_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(num_tiles, tile_total, tile_offset, ranges, info);
     return cudaGetLastError();
 }
@@ -464,13 +482,9 @@ cudaError_t launch_tile_sort_pack(int num_tiles, int max_count, int R, const uin
     constexpr size_t large_smem = (size_t)(SORT_LARGE_KEYS + SORT_LARGE_KEYS / 16) * sizeof(uint64_t);
     tile_sort_kernel<false><<<num_tiles, SORT_SMALL_THREADS, small_smem, stream>>>(ranges, keys, point_list, grec, recs);
     if (max_count > SORT_SMALL_KEYS) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(tile_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)large_smem);
-            if (e != cudaSuccess) return e;
-            attr_set = true;
-        }
+        static PerDeviceOnce once;
+        cudaError_t e = ensure_dynamic_smem(tile_sort_kernel<true>, (int)large_smem, once);
+        if (e != cudaSuccess) return e;
         tile_sort_kernel<true><<<num_tiles, SORT_LARGE_THREADS, large_smem, stream>>>(ranges, keys, point_list, grec, recs);
     }
     return cudaGetLastError();

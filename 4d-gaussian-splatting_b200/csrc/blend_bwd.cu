@@ -621,13 +621,9 @@ cudaError_t launch_blend_bwd(const BlendBwdParams& p, cudaStream_t stream) {
     if (blend_bwd_is_raw(p)) {
         // colour fragments in shared memory + 3 stages: 64 registers, 53 KB -> 4 CTAs / SM.  (Keeping them in
         // registers costs 80 registers -> 3 CTAs / SM and measured 8 % slower.)
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(blend_bwd2_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)sizeof(B2Smem<3, true>));
-            if (e != cudaSuccess) return e;
-            attr_set = true;
-        }
+        static PerDeviceOnce once;
+        cudaError_t e = ensure_dynamic_smem(blend_bwd2_kernel<3, true>, (int)sizeof(B2Smem<3, true>), once);
+        if (e != cudaSuccess) return e;
         blend_bwd2_kernel<3, true><<<grid, B2_THREADS, sizeof(B2Smem<3, true>), stream>>>(p);
     } else if (!p.dL_depths && !p.dL_masks && !p.dL_dpix_flow) {
         blend_bwd_kernel<false><<<grid, BB_THREADS, 0, stream>>>(p);

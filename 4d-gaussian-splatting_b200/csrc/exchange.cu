@@ -54,7 +54,41 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const PackTable tb, cons
     }
 }
 
+// Guard of the sparse exchange: rows of Gaussians outside the union are assumed to be zero on every rank (true for
+// the rasterizer's gradients, false for e.g. a rigidity loss over all Gaussians, reference train.py:132-152).  One
+// pass over the (small) geometry gradients; the caller reads the flag together with the union size.
+struct CheckTable {
+    const float* tensor[FDGS_MAX_PACK];
+    int width[FDGS_MAX_PACK];
+};
+__global__ void __launch_bounds__(256) rows_zero_check_kernel(const CheckTable tb, long long P, const int* __restrict__ radii,
+                                                              int* __restrict__ flag) {
+    const int t = blockIdx.y;
+    const int w = tb.width[t];
+    const float* __restrict__ ten = tb.tensor[t];
+    bool bad = false;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < P; r += (long long)gridDim.x * blockDim.x) {
+        if (radii[r] > 0) continue;
+        for (int c = 0; c < w; ++c) bad |= (ten[r * w + c] != 0.f);
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
 }  // namespace
+
+cudaError_t launch_rows_zero_check(int n, const float* const* tensors, const int* widths, long long P, const int* mask_radii,
+                                   int* flag, cudaStream_t stream) {
+    if (n <= 0 || P <= 0) return cudaSuccess;
+    CheckTable tb;
+    for (int i = 0; i < n; ++i) {
+        tb.tensor[i] = tensors[i];
+        tb.width[i] = widths[i];
+    }
+    long long blocks = (P + 255) / 256;
+    if (blocks > device_sm_count() * 8) blocks = device_sm_count() * 8;
+    rows_zero_check_kernel<<<dim3((unsigned)blocks, (unsigned)n, 1), 256, 0, stream>>>(tb, P, mask_radii, flag);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_pack_rows(bool unpack, int n, float* const* tensors, const int* widths, const long long* block_off,
                              const long long* idx, long long K, float* flat, cudaStream_t stream) {
@@ -72,7 +106,7 @@ cudaError_t launch_pack_rows(bool unpack, int n, float* const* tensors, const in
         if (work > widest) widest = work;
     }
     long long blocks = (widest + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;   // grid-stride beyond 16 CTAs per SM
+    if (blocks > device_sm_count() * 16) blocks = device_sm_count() * 16;   // grid-stride beyond 16 CTAs per SM
     dim3 grid((unsigned)blocks, (unsigned)n, 1);
     if (unpack) pack_rows_kernel<true><<<grid, 256, 0, stream>>>(tb, idx, K, flat);
     else pack_rows_kernel<false><<<grid, 256, 0, stream>>>(tb, idx, K, flat);

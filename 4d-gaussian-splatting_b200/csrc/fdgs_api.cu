@@ -10,6 +10,7 @@
 #include <mutex>
 #include <string>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost nothing unless a profiler is attached
 #include "../../include/fdgs.h"
 #include "fdgs_internal.h"
 
@@ -37,6 +38,7 @@ struct ProfEvent {
 std::mutex g_prof_mu;
 bool g_prof_on = false;
 std::vector<ProfEvent> g_prof_events;
+constexpr size_t kMaxProfEvents = 4096;
 std::atomic<long long> g_kernel_launches{0};
 // FDGS_TRACE=1 + debug=true: print every stage to stderr before and after its synchronisation
 const bool g_trace = getenv("FDGS_TRACE") != nullptr;
@@ -45,19 +47,31 @@ struct StageTimer {
     cudaEvent_t a = nullptr, b = nullptr;
     int stage;
     cudaStream_t stream;
-    StageTimer(int stage_, cudaStream_t s) : stage(stage_), stream(s) {
+    StageTimer(int stage_, cudaStream_t s, const char* name) : stage(stage_), stream(s) {
+        nvtxRangePushA(name);   // one NVTX range per pipeline stage (nsys / ncu --nvtx)
         if (g_prof_on) {
             cudaEventCreate(&a);
             cudaEventCreate(&b);
             cudaEventRecord(a, stream);
         }
     }
+    bool open = true;
+    ~StageTimer() {
+        if (open) nvtxRangePop();   // error return between start and stop
+    }
     void stop(int kernels) {
+        nvtxRangePop();
+        open = false;
         g_kernel_launches += kernels;
         if (a) {
             cudaEventRecord(b, stream);
             std::lock_guard<std::mutex> lk(g_prof_mu);
-            g_prof_events.push_back({stage, a, b});
+            if (g_prof_events.size() < kMaxProfEvents) {
+                g_prof_events.push_back({stage, a, b});
+            } else {   // nobody is reading (fdgs_profile_read): do not grow without bound
+                cudaEventDestroy(a);
+                cudaEventDestroy(b);
+            }
         }
     }
 };
@@ -65,7 +79,7 @@ struct StageTimer {
 // FDGS_STAGE(stage id, kernels launched, launch expression, name)
 #define FDGS_STAGE(sid, nk, expr, what)                                                               \
     do {                                                                                              \
-        StageTimer _t(sid, stream);                                                                   \
+        StageTimer _t(sid, stream, what);                                                                \
         FDGS_CUDA(expr, what);                                                                        \
         _t.stop(nk);                                                                                  \
         if (debug) {                                                                                  \
@@ -120,7 +134,7 @@ struct ImageState {
     uint32_t* bin_matrix;    // [bin_ctas][tiles] per-CTA tile histograms -> column prefixes
     uint32_t* tile_total;    // [tiles]
     uint32_t* tile_offset;   // [tiles]
-    uint32_t* bin_info;      // [2] total instances, largest tile
+    uint32_t* bin_info;      // [4] total instances, largest tile, overflow flag, spare
     size_t tiles;
     size_t bytes;
     static ImageState carve(char* base, int W, int H) {
@@ -134,7 +148,7 @@ struct ImageState {
         s.bin_matrix = c.take<uint32_t>(s.tiles * (size_t)fdgs::bin_ctas());
         s.tile_total = c.take<uint32_t>(s.tiles);
         s.tile_offset = c.take<uint32_t>(s.tiles);
-        s.bin_info = c.take<uint32_t>(2);
+        s.bin_info = c.take<uint32_t>(4);
         s.bytes = c.total();
         return s;
     }
@@ -161,11 +175,13 @@ char* align128(char* p) {
     return reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(p) + 127) & ~(uintptr_t)127);
 }
 
-void sh_staging(const float* shs, int M, int* bulk_ok, int* stride_floats) {
+// `whole_blocks`: the forward reads a row in whole 16-coefficient blocks (RowSmem::load_block, 12 float4 each), so
+// its staged path needs M % 16 == 0; the backward bounds its accesses by the row length and only needs M % 4 == 0.
+void sh_staging(const float* shs, int M, bool whole_blocks, int* bulk_ok, int* stride_floats) {
     *bulk_ok = 0;
     *stride_floats = 0;
     if (!shs || M <= 0) return;
-    if ((M % 4) != 0 || (reinterpret_cast<uintptr_t>(shs) % 16) != 0) return;
+    if ((M % (whole_blocks ? 16 : 4)) != 0 || (reinterpret_cast<uintptr_t>(shs) % 16) != 0) return;
     int q = (3 * M) / 4 + 1;   // 16-byte units incl. padding
     if ((q & 1) == 0) ++q;     // odd stride in 16-byte units -> conflict-free LDS.128 / STS.128
     if ((size_t)q * 16 * 128 > 200 * 1024) return;
@@ -195,6 +211,9 @@ int fdgs_forward(const fdgs_forward_args* a, fdgs_alloc_fn geom_alloc, void* geo
     const bool debug = a->debug != 0;
     const int P = a->P, W = a->width, H = a->height;
     if (P < 0 || W <= 0 || H <= 0) return fail(FDGS_ERR_INVALID_ARG, "bad P / width / height");
+    // the blend kernel writes every pixel of every image even when nothing is rendered (P == 0: background only)
+    if (!a->out_color || !a->out_flow || !a->out_depth || !a->out_T || !a->background)
+        return fail(FDGS_ERR_INVALID_ARG, "background and the output images must be set");
     if (P > 0) {
         if (!a->means3D || !a->opacities || !a->viewmatrix || !a->projmatrix || !a->cam_pos || !a->background)
             return fail(FDGS_ERR_INVALID_ARG, "means3D/opacities/viewmatrix/projmatrix/cam_pos/background must be set");
@@ -255,7 +274,7 @@ int fdgs_forward(const fdgs_forward_args* a, fdgs_alloc_fn geom_alloc, void* geo
         pp.focal_y = H / (2.0f * a->tan_fovy);
         pp.focal_x = W / (2.0f * a->tan_fovx);
         pp.grid_x = grid_x; pp.grid_y = grid_y; pp.prefiltered = a->prefiltered;
-        sh_staging(a->colors_precomp ? nullptr : a->shs, a->M, &pp.sh_bulk_ok, &pp.sh_row_stride_floats);
+        sh_staging(a->colors_precomp ? nullptr : a->shs, a->M, true, &pp.sh_bulk_ok, &pp.sh_row_stride_floats);
         pp.flows = a->flows_precomp;
         pp.out_means3D = a->out_means3D; pp.radii = a->radii; pp.cov3D = geom.cov3D; pp.grec = geom.grec;
         pp.clamped = geom.clamped; pp.tiles_touched = geom.tiles_touched; pp.binrec = geom.binrec;
@@ -271,11 +290,12 @@ int fdgs_forward(const fdgs_forward_args* a, fdgs_alloc_fn geom_alloc, void* geo
                }(),
                "bin_count + tile_scan");
     // the one host synchronisation of the forward (reference: rasterizer_impl.cu:302)
-    int bin_info[2] = {0, 0};
+    int bin_info[4] = {0, 0, 0, 0};
     FDGS_CUDA(cudaMemcpyAsync(bin_info, img.bin_info, sizeof(bin_info), cudaMemcpyDeviceToHost, stream), "num_rendered copy");
     FDGS_CUDA(cudaStreamSynchronize(stream), "num_rendered sync");
     num_rendered = bin_info[0];
-    if (num_rendered < 0) return fail(FDGS_ERR_UNSUPPORTED, "more than 2^31 tile instances");
+    // bin_info[2]: the 64-bit total computed on the device exceeded 2^31 - 1 (a wrapped 32-bit total would look valid)
+    if (num_rendered < 0 || bin_info[2] != 0) return fail(FDGS_ERR_UNSUPPORTED, "more than 2^31 - 1 tile instances");
     res->num_rendered = num_rendered;
 
     const size_t bin_bytes = fdgs_binning_bytes(num_rendered, W, H);
@@ -315,6 +335,9 @@ int fdgs_backward(const fdgs_backward_args* a, void* stream_v) {
         return fail(FDGS_ERR_INVALID_ARG, "scratch buffers of the forward pass required");
     // dL_depths / dL_masks / dL_dpix_flow may be NULL: no upstream gradient for that image
     if (!a->dL_dpix) return fail(FDGS_ERR_INVALID_ARG, "colour image gradient required");
+    if (!a->background || !a->radii || !a->out_means3D || !a->viewmatrix || !a->projmatrix || !a->campos)
+        return fail(FDGS_ERR_INVALID_ARG, "background / radii / out_means3D / viewmatrix / projmatrix / campos required");
+    if (a->sh_factors && a->dL_dsh) return fail(FDGS_ERR_INVALID_ARG, "sh_factors and dL_dsh are mutually exclusive");
     if (!a->dL_dmean2D || !a->dL_dconic || !a->dL_dopacity || !a->dL_dcolor || !a->dL_dflows || !a->dL_dmean3D ||
         !a->dL_dcov3D || !a->dL_dts || !a->dL_dscale || !a->dL_dscale_t || !a->dL_drot || !a->dL_drot_r)
         return fail(FDGS_ERR_INVALID_ARG, "gradient outputs required");
@@ -351,10 +374,11 @@ int fdgs_backward(const fdgs_backward_args* a, void* stream_v) {
     pb.rot_4d = a->rot_4d; pb.gaussian_dim = a->gaussian_dim; pb.force_sh_3d = a->force_sh_3d;
     pb.has_scales = (a->scales != nullptr) ? 1 : 0;
     pb.grec = geom.grec; pb.blend_raw = blend_raw ? 1 : 0; pb.W = W; pb.H = H;
-    sh_staging(a->shs, a->M, &pb.sh_bulk_ok, &pb.sh_row_stride_floats);
+    sh_staging(a->shs, a->M, false, &pb.sh_bulk_ok, &pb.sh_row_stride_floats);
     if (a->dL_dsh && (reinterpret_cast<uintptr_t>(a->dL_dsh) % 16) != 0) pb.sh_bulk_ok = 0;
     pb.dL_dmean2D = a->dL_dmean2D; pb.dL_dconic = a->dL_dconic; pb.dL_dopacity = a->dL_dopacity; pb.dL_dcolor = a->dL_dcolor;
-    pb.dL_dmean3D = a->dL_dmean3D; pb.dL_dcov3D = a->dL_dcov3D; pb.dL_dsh = a->dL_dsh; pb.dL_dts = a->dL_dts;
+    pb.dL_dmean3D = a->dL_dmean3D; pb.dL_dcov3D = a->dL_dcov3D; pb.dL_dsh = a->dL_dsh; pb.sh_factors = a->sh_factors;
+    pb.dL_dts = a->dL_dts;
     pb.dL_dscale = a->dL_dscale; pb.dL_dscale_t = a->dL_dscale_t; pb.dL_drot = a->dL_drot; pb.dL_drot_r = a->dL_drot_r;
     if (pb.has_scales && pb.rot_4d && (!a->rotations_r || !a->scales_t || !a->ts || !a->opacities))
         return fail(FDGS_ERR_INVALID_ARG, "rot_4d backward needs rotations_r, scales_t, ts, opacities");
@@ -393,6 +417,46 @@ int fdgs_pack_rows(int n, const float* const* tensors, const int* widths, const 
 int fdgs_unpack_rows(int n, float* const* tensors, const int* widths, const long long* block_off, const long long* idx,
                      long long K, const float* flat, void* stream) {
     return pack_common(true, n, tensors, widths, block_off, idx, K, const_cast<float*>(flat), stream);
+}
+
+int fdgs_sh_outer_sum(const fdgs_sh_sum_args* a, void* stream_v) {
+    g_last_error.clear();
+    if (!a) return fail(FDGS_ERR_INVALID_ARG, "null argument");
+    if (a->P <= 0) return FDGS_OK;
+    if (a->V < 0 || a->K < 0 || a->M <= 0 || a->m0 <= 0 || a->m0 > a->M || a->D < 0 || a->D > 3 || a->D_t < 0 || a->D_t > 2)
+        return fail(FDGS_ERR_INVALID_ARG, "bad V / K / M / m0 / degrees");
+    if (!a->slot_of || !a->means3D || !a->out0 || (a->m0 < a->M && !a->out1) || (a->V > 0 && a->K > 0 && !a->table))
+        return fail(FDGS_ERR_INVALID_ARG, "slot_of / means3D / table / outputs required");
+    if (a->rot_4d && (!a->scales || !a->scales_t || !a->rotations || !a->rotations_r || !a->ts))
+        return fail(FDGS_ERR_INVALID_ARG, "rot_4d needs scales, scales_t, rotations, rotations_r, ts");
+    const bool sh4d = !(a->gaussian_dim == 3 || a->force_sh_3d);
+    if (sh4d && !a->ts) return fail(FDGS_ERR_INVALID_ARG, "4D SH needs ts");
+    if (a->V > 0 && (a->meta_off < 3ll * a->K || a->view_stride < a->meta_off + 4))
+        return fail(FDGS_ERR_INVALID_ARG, "view block too small for K rows + metadata");
+    fdgs::ShSumParams p;
+    p.P = a->P; p.V = a->V; p.K = a->K; p.table = a->table; p.view_stride = a->view_stride; p.meta_off = a->meta_off;
+    p.slot_of = a->slot_of; p.means3D = a->means3D; p.ts = a->ts; p.scales = a->scales; p.scales_t = a->scales_t;
+    p.rotations = a->rotations; p.rotations_r = a->rotations_r; p.scale_modifier = a->scale_modifier;
+    p.time_duration = a->time_duration; p.rot_4d = a->rot_4d; p.gaussian_dim = a->gaussian_dim;
+    p.force_sh_3d = a->force_sh_3d; p.D = a->D; p.D_t = a->D_t; p.M = a->M;
+    p.out0 = a->out0; p.m0 = a->m0; p.out1 = (a->m0 < a->M) ? a->out1 : nullptr; p.accumulate = a->accumulate;
+    FDGS_CUDA(fdgs::launch_sh_outer_sum(p, reinterpret_cast<cudaStream_t>(stream_v)), "sh_outer_sum");
+    g_kernel_launches += 1;
+    return FDGS_OK;
+}
+
+int fdgs_check_rows_zero(int n, const float* const* tensors, const int* widths, long long P, const int* radii, int* flag,
+                         void* stream_v) {
+    g_last_error.clear();
+    if (n < 0 || n > FDGS_MAX_PACK || P < 0) return fail(FDGS_ERR_INVALID_ARG, "bad tensor count / row count");
+    if (n == 0 || P == 0) return FDGS_OK;
+    if (!tensors || !widths || !radii || !flag) return fail(FDGS_ERR_INVALID_ARG, "null argument");
+    for (int i = 0; i < n; ++i)
+        if (!tensors[i] || widths[i] <= 0) return fail(FDGS_ERR_INVALID_ARG, "bad tensor table entry");
+    FDGS_CUDA(fdgs::launch_rows_zero_check(n, tensors, widths, P, radii, flag, reinterpret_cast<cudaStream_t>(stream_v)),
+              "rows_zero_check");
+    g_kernel_launches += 1;
+    return FDGS_OK;
 }
 
 int fdgs_profile_enable(int on) {

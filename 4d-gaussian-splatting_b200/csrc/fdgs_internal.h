@@ -3,9 +3,31 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include "fdgs_common.cuh"
 
 namespace fdgs {
+
+// ---- per-device launch configuration -------------------------------------------------------------
+// Function attributes (the > 48 KB dynamic shared-memory opt-in) belong to the (function, device) pair, so a
+// process that renders on several GPUs has to set them once on EACH device; the flag word is per call site, one
+// bit per device ordinal, updated atomically (two racing threads both set the idempotent attribute -- harmless).
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> done{0ull};
+};
+template <class Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, int bytes, PerDeviceOnce& once) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (dev < 64 && (once.done.load(std::memory_order_acquire) & bit)) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev < 64) once.done.fetch_or(bit, std::memory_order_release);
+    return e;
+}
+// SM count of the current device (148 on a B200), cached per device ordinal
+int device_sm_count();
 
 // ---- forward preprocess ---------------------------------------------------------------------
 struct PreprocessFwdParams {
@@ -135,7 +157,8 @@ struct PreprocessBwdParams {
     int W, H;
     float* dL_dmean3D;
     float* dL_dcov3D;
-    float* dL_dsh;
+    float* dL_dsh;          // [P,M,3], or NULL when sh_factors is set
+    float* sh_factors;      // [P,3] clamp-masked colour gradient (view-parallel mode) instead of the dL_dsh rows
     float* dL_dts;
     float* dL_dscale;
     float* dL_dscale_t;
@@ -144,6 +167,31 @@ struct PreprocessBwdParams {
 };
 cudaError_t launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream);
 int preprocess_bwd_kernel_count(const PreprocessBwdParams& p);
+
+// ---- view-parallel SH gradient (preprocess_bwd.cu: sh_outer_sum_kernel) -----------------------------------------
+struct ShSumParams {
+    int P, V, K;
+    const float* table;       // [V][view_stride] floats: K rows of 3 (clamp-masked colour gradient), then metadata
+    long long view_stride;    // floats per view block
+    long long meta_off;       // offset of the view's metadata inside its block: timestamp, campos x, y, z
+    const int* slot_of;       // [P] row of the Gaussian inside a view block, -1 = rendered by no view
+    const float* means3D;     // replicated Gaussian parameters, as handed to the rasterizer
+    const float* ts;
+    const float* scales;
+    const float* scales_t;
+    const float* rotations;
+    const float* rotations_r;
+    float scale_modifier, time_duration;
+    int rot_4d, gaussian_dim, force_sh_3d, D, D_t, M;
+    float* out0;              // [P, m0, 3]
+    int m0;                   // coefficients 0 .. m0-1 of a row live in out0 ...
+    float* out1;              // ... the rest in out1 [P, M - m0, 3] (NULL when m0 == M)
+    int accumulate;           // add to the tensors' contents instead of overwriting them
+};
+cudaError_t launch_sh_outer_sum(const ShSumParams& p, cudaStream_t stream);
+// flag[0] |= 1 if any row r with mask[r] == 0 of any of the n tensors has a non-zero element
+cudaError_t launch_rows_zero_check(int n, const float* const* tensors, const int* widths, long long P, const int* mask_radii,
+                                   int* flag, cudaStream_t stream);
 
 cudaError_t launch_pack_rows(bool unpack, int n, float* const* tensors, const int* widths, const long long* block_off,
                              const long long* idx, long long K, float* flat, cudaStream_t stream);

@@ -132,6 +132,7 @@ __device__ __forceinline__ void sh_ctx_init(const PreprocessBwdParams& a, int id
 
 // Consumes the SH row held in `rowq` (float4, in place) and replaces it by the dL_dsh row.
 // Returns the direction sums and the temporal term.  NQ = number of float4 in the row (3*M/4).
+template <bool WRITE = true>
 __device__ __forceinline__ void sh_row_inplace(float4* rowq, int nq, const ShCtx& c, float& ddx, float& ddy,
                                                float& ddz, float& dtt) {
     const int ngroups = nq / 3;   // groups of 4 coefficients
@@ -178,9 +179,11 @@ __device__ __forceinline__ void sh_row_inplace(float4* rowq, int nq, const ShCtx
                 o[3 * j + 1] = w * c.dRGB[1];
                 o[3 * j + 2] = w * c.dRGB[2];
             }
-            rowq[3 * G + 0] = make_float4(o[0], o[1], o[2], o[3]);
-            rowq[3 * G + 1] = make_float4(o[4], o[5], o[6], o[7]);
-            rowq[3 * G + 2] = make_float4(o[8], o[9], o[10], o[11]);
+            if (WRITE) {
+                rowq[3 * G + 0] = make_float4(o[0], o[1], o[2], o[3]);
+                rowq[3 * G + 1] = make_float4(o[4], o[5], o[6], o[7]);
+                rowq[3 * G + 2] = make_float4(o[8], o[9], o[10], o[11]);
+            }
         }
     }
     ddx = ddy = ddz = dtt = 0.f;
@@ -194,11 +197,17 @@ __device__ __forceinline__ void sh_row_inplace(float4* rowq, int nq, const ShCtx
         }
     }
     // coefficients beyond the three 16-blocks (M > 48) are never used: zero gradient
-    for (int qi = 36; qi < nq; ++qi) rowq[qi] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (WRITE)
+        for (int qi = 36; qi < nq; ++qi) rowq[qi] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // ---- SH backward ----------------------------------------------------------------------------------
-template <bool BULK>
+// FACTORS (multi-GPU view parallelism, fdgs/dist.py): the dL_dsh row of a view is the outer product
+// (basis weights of the view direction and time) x (clamp-masked colour gradient), so instead of the 12*M-byte row
+// only the 3-float colour factor is written (sh_factors[P,3], zeros for Gaussians this view did not render); the rows
+// of all views are rebuilt and summed after the exchange by sh_outer_sum_kernel (exchange.cu).  The SH row is still
+// read: the direction / time gradients need sum_k dbasis_k (sh_k . dRGB).
+template <bool BULK, bool FACTORS>
 __global__ void __launch_bounds__(SB_THREADS, 6) sh_bwd_kernel(const PreprocessBwdParams a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
@@ -231,7 +240,13 @@ __global__ void __launch_bounds__(SB_THREADS, 6) sh_bwd_kernel(const PreprocessB
     __syncthreads();
 
     // zero rows: every float4 of every non-rendered row of this CTA, coalesced
-    {
+    if (FACTORS) {
+        if (in_range && !vis) {
+            a.sh_factors[3 * idx + 0] = 0.f;
+            a.sh_factors[3 * idx + 1] = 0.f;
+            a.sh_factors[3 * idx + 2] = 0.f;
+        }
+    } else {
         const int rows_here = min(SB_THREADS, a.P - blockIdx.x * SB_THREADS);
         float4* dst = reinterpret_cast<float4*>(a.dL_dsh + (size_t)blockIdx.x * SB_THREADS * row_floats);
         const int total = rows_here * nq;
@@ -250,7 +265,14 @@ __global__ void __launch_bounds__(SB_THREADS, 6) sh_bwd_kernel(const PreprocessB
     }
 
     ShCtx c;
-    if (vis) sh_ctx_init(a, idx, c);
+    if (vis) {
+        sh_ctx_init(a, idx, c);
+        if (FACTORS) {
+            a.sh_factors[3 * idx + 0] = c.dRGB[0];
+            a.sh_factors[3 * idx + 1] = c.dRGB[1];
+            a.sh_factors[3 * idx + 2] = c.dRGB[2];
+        }
+    }
 
     if (BULK) {
         float* rows = reinterpret_cast<float*>(smem_raw);
@@ -260,7 +282,7 @@ __global__ void __launch_bounds__(SB_THREADS, 6) sh_bwd_kernel(const PreprocessB
             float4* rowq = reinterpret_cast<float4*>(rows + (size_t)(my_rank - lo) * a.sh_row_stride_floats);
             if (round > 0) {
                 // the previous round's bulk stores must have finished reading the slots
-                if (vis) bulk_wait_read_all();
+                if (!FACTORS && vis) bulk_wait_read_all();
                 __syncthreads();
             }
             if (tid == 0) mbar_expect_tx(&bar, (uint32_t)cnt * (uint32_t)row_floats * 4u);
@@ -268,10 +290,12 @@ __global__ void __launch_bounds__(SB_THREADS, 6) sh_bwd_kernel(const PreprocessB
             if (mine) {
                 mbar_wait(&bar, (uint32_t)round & 1u);
                 float ddx, ddy, ddz, dtt;
-                sh_row_inplace(rowq, nq, c, ddx, ddy, ddz, dtt);
-                fence_async_smem();
-                bulk_s2g(a.dL_dsh + (size_t)idx * row_floats, rowq, (uint32_t)row_floats * 4u);
-                bulk_commit();
+                sh_row_inplace<!FACTORS>(rowq, nq, c, ddx, ddy, ddz, dtt);
+                if (!FACTORS) {
+                    fence_async_smem();
+                    bulk_s2g(a.dL_dsh + (size_t)idx * row_floats, rowq, (uint32_t)row_floats * 4u);
+                    bulk_commit();
+                }
                 const float3 dm = dnormvdv3(c.dir_orig, make_float3(ddx, ddy, ddz));
                 a.dL_dmean3D[3 * idx + 0] = dm.x;
                 a.dL_dmean3D[3 * idx + 1] = dm.y;
@@ -279,11 +303,11 @@ __global__ void __launch_bounds__(SB_THREADS, 6) sh_bwd_kernel(const PreprocessB
                 a.dL_dts[idx] = c.sh4d ? dtt : 0.f;
             }
         }
-        if (vis) bulk_wait_all();
+        if (!FACTORS && vis) bulk_wait_all();
     } else if (vis) {
         // generic path: global loads / stores, one coefficient at a time
         const float* grow = a.shs + (size_t)idx * row_floats;
-        float* drow = a.dL_dsh + (size_t)idx * row_floats;
+        float* drow = FACTORS ? nullptr : a.dL_dsh + (size_t)idx * row_floats;
         float ddx = 0.f, ddy = 0.f, ddz = 0.f, dtt = 0.f;
         ShDeriv SDg;
         sh_basis_deriv(c.dirn.x, c.dirn.y, c.dirn.z, c.deg, SDg);
@@ -299,9 +323,11 @@ __global__ void __launch_bounds__(SB_THREADS, 6) sh_bwd_kernel(const PreprocessB
                     sx += SDg.dx[k] * sk; sy += SDg.dy[k] * sk; sz += SDg.dz[k] * sk; sl += SDg.l[k] * sk;
                     w = (blk == 0) ? ((c.sh4d && k == 1) ? SDg.l[0] : SDg.l[k]) : c.tw[blk < 3 ? blk : 0] * SDg.l[k];
                 }
-                drow[3 * cidx + 0] = w * c.dRGB[0];
-                drow[3 * cidx + 1] = w * c.dRGB[1];
-                drow[3 * cidx + 2] = w * c.dRGB[2];
+                if (!FACTORS) {
+                    drow[3 * cidx + 0] = w * c.dRGB[0];
+                    drow[3 * cidx + 1] = w * c.dRGB[1];
+                    drow[3 * cidx + 2] = w * c.dRGB[2];
+                }
             }
             if (blk_on) {
                 ddx += c.tw[blk] * sx; ddy += c.tw[blk] * sy; ddz += c.tw[blk] * sz;
@@ -313,6 +339,130 @@ __global__ void __launch_bounds__(SB_THREADS, 6) sh_bwd_kernel(const PreprocessB
         a.dL_dmean3D[3 * idx + 1] = dm.y;
         a.dL_dmean3D[3 * idx + 2] = dm.z;
         a.dL_dts[idx] = c.sh4d ? dtt : 0.f;
+    }
+}
+
+// ---- view-parallel SH gradient: rebuild and sum the rows of all views -------------------------------------------
+// dL_dsh of ONE view is rank one per Gaussian: row[k][ch] = w_k(view direction, time) * dRGB[ch]  (sh_row_inplace
+// above).  With the views of a step spread over ranks (fdgs/dist.py) only dRGB travels (3 floats per Gaussian and
+// view, all-gathered for the union of rendered Gaussians); every rank then rebuilds w_k for every view from the
+// REPLICATED Gaussian parameters and the view's (timestamp, camera position) and sums the outer products in global
+// view order -- 12 bytes per (Gaussian, view) on NVLink instead of a 576-byte row in an all-reduce, and the sum is
+// bit-identical to accumulating the views' dL_dsh one after the other (what the reference's sequential loop does,
+// train.py:104-166): explicit round-to-nearest multiply then add, no fused rounding.
+// The direction is the one sh_ctx_init() sees: the time-shifted mean the forward wrote to out_means3D
+// (preprocess_fwd.cu: mean + dt * Sigma_xyz,t / Sigma_tt, same intrinsics, same order) minus the camera position.
+// 4 threads per Gaussian, thread kg owns the coefficients 4 kg .. 4 kg + 3 of each of the three 16-blocks.
+__global__ void __launch_bounds__(128) sh_outer_sum_kernel(const ShSumParams a) {
+    const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int idx = (int)(gt >> 2), kg = (int)(gt & 3);
+    if (idx >= a.P) return;
+    const int slot = a.slot_of[idx];
+    float acc[3][12];
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int i = 0; i < 12; ++i) acc[b][i] = 0.f;
+
+    if (slot >= 0) {
+        const bool sh4d = !((a.gaussian_dim == 3) || a.force_sh_3d);
+        const int ncoef = (a.D + 1) * (a.D + 1);
+        const float ox = a.means3D[3 * idx + 0], oy = a.means3D[3 * idx + 1], oz = a.means3D[3 * idx + 2];
+        const float t_g = (a.ts != nullptr) ? a.ts[idx] : 0.f;
+        float s03 = 0.f, s13 = 0.f, s23 = 0.f, cov_t = 1.f;
+        if (a.rot_4d) {
+            const float mod = a.scale_modifier;
+            Sigma4 S;
+            build_M4(fmul(mod, a.scales[3 * idx + 0]), fmul(mod, a.scales[3 * idx + 1]), fmul(mod, a.scales[3 * idx + 2]),
+                     fmul(mod, a.scales_t[idx]), reinterpret_cast<const float4*>(a.rotations)[idx],
+                     reinterpret_cast<const float4*>(a.rotations_r)[idx], S.M);
+            sigma_from_M(S);
+            s03 = S.s03; s13 = S.s13; s23 = S.s23; cov_t = S.s33;
+        }
+        for (int v = 0; v < a.V; ++v) {
+            const float* blk = a.table + (size_t)v * a.view_stride;
+            const float r = blk[3 * (size_t)slot + 0], g = blk[3 * (size_t)slot + 1], b = blk[3 * (size_t)slot + 2];
+            if (r == 0.f && g == 0.f && b == 0.f) continue;   // not rendered by view v (or a zero colour gradient)
+            const float* meta = blk + a.meta_off;             // timestamp, camera position
+            const float timestamp = meta[0];
+            float mx = ox, my = oy, mz = oz;
+            if (a.rot_4d) {
+                const float dt = fsub(timestamp, t_g);
+                mx = ffma(dt, fdiv(s03, cov_t), mx);
+                my = ffma(dt, fdiv(s13, cov_t), my);
+                mz = ffma(dt, fdiv(s23, cov_t), mz);
+            }
+            // exactly sh_ctx_init()
+            const float dx = mx - meta[1], dy = my - meta[2], dz = mz - meta[3];
+            const float len = sqrtf(dx * dx + dy * dy + dz * dz);
+            float gx = dx / len, gy = dy / len, gz = dz / len;
+            float tw1 = 0.f, tw2 = 0.f;
+            int nblk = 1;
+            if (sh4d && a.D > 2 && a.D_t > 0) {
+                const float dir_t = t_g - timestamp;
+                tw1 = (float)cos(2 * FDGS_MY_PI * (double)dir_t / (double)a.time_duration);
+                nblk = 2;
+                if (a.D_t > 1) {
+                    tw2 = (float)cos(2 * FDGS_MY_PI * (double)dir_t * 2 / (double)a.time_duration);
+                    nblk = 3;
+                }
+            }
+            ShDeriv S;
+            sh_basis_deriv(gx, gy, gz, a.D, S);
+            const float drgb[3] = {r, g, b};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {   // select l[4 kg + j] without dynamic register indexing
+                    if (q != kg) continue;
+                    const int k = 4 * q + j;
+                    if (k >= ncoef) continue;
+                    const float lk = S.l[k];
+                    const float w0 = (sh4d && k == 1) ? S.l[0] : lk;
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        acc[0][3 * j + ch] = __fadd_rn(acc[0][3 * j + ch], __fmul_rn(w0, drgb[ch]));
+                        if (nblk > 1) acc[1][3 * j + ch] = __fadd_rn(acc[1][3 * j + ch], __fmul_rn(__fmul_rn(tw1, lk), drgb[ch]));
+                        if (nblk > 2) acc[2][3 * j + ch] = __fadd_rn(acc[2][3 * j + ch], __fmul_rn(__fmul_rn(tw2, lk), drgb[ch]));
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- store: coefficients 16 b + 4 kg + j of row idx; the row may be split over two tensors (features_dc |
+    // features_rest of the reference's GaussianModel, scene/gaussian_model.py:210-214) ------------------------------
+    const int M = a.M, m0 = a.m0;
+    if (a.out1 == nullptr && (M % 4) == 0 && !a.accumulate) {
+        float4* row = reinterpret_cast<float4*>(a.out0 + (size_t)idx * 3 * M);
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            if (16 * b + 4 * kg + 3 < M) {
+                float4* dst = row + (48 * b + 12 * kg) / 4;
+                dst[0] = make_float4(acc[b][0], acc[b][1], acc[b][2], acc[b][3]);
+                dst[1] = make_float4(acc[b][4], acc[b][5], acc[b][6], acc[b][7]);
+                dst[2] = make_float4(acc[b][8], acc[b][9], acc[b][10], acc[b][11]);
+            }
+        }
+        // coefficients beyond the three 16-blocks are never used: zero gradient
+        for (int q = 36 + kg; q < 3 * M / 4; q += 4) row[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = 16 * b + 4 * kg + j;
+                if (c >= M) continue;
+                float* dst = (c < m0) ? a.out0 + ((size_t)idx * m0 + c) * 3 : a.out1 + ((size_t)idx * (M - m0) + (c - m0)) * 3;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) dst[ch] = a.accumulate ? dst[ch] + acc[b][3 * j + ch] : acc[b][3 * j + ch];
+            }
+        }
+        if (!a.accumulate)
+            for (int c = 48 + kg; c < M; c += 4) {
+                float* dst = (c < m0) ? a.out0 + ((size_t)idx * m0 + c) * 3 : a.out1 + ((size_t)idx * (M - m0) + (c - m0)) * 3;
+                dst[0] = dst[1] = dst[2] = 0.f;
+            }
     }
 }
 
@@ -599,31 +749,38 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means, cons
 }  // namespace
 
 int preprocess_bwd_kernel_count(const PreprocessBwdParams& p) {
-    return (p.shs != nullptr && p.M > 0 && p.dL_dsh != nullptr) ? 2 : 1;
+    return (p.shs != nullptr && p.M > 0 && (p.dL_dsh != nullptr || p.sh_factors != nullptr)) ? 2 : 1;
 }
 
 cudaError_t launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream) {
     if (p.P <= 0) return cudaSuccess;
-    const bool has_sh = p.shs != nullptr && p.M > 0 && p.dL_dsh != nullptr;
+    const bool factors = p.sh_factors != nullptr;
+    const bool has_sh = p.shs != nullptr && p.M > 0 && (p.dL_dsh != nullptr || factors);
     if (has_sh) {
         const int blocks = (p.P + SB_THREADS - 1) / SB_THREADS;
         if (p.sh_bulk_ok) {
             const size_t smem = (size_t)SB_CAP * p.sh_row_stride_floats * sizeof(float);
-            static bool attr_set = false;
-            if (!attr_set) {
-                cudaError_t e = cudaFuncSetAttribute(sh_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     200 * 1024);
-                if (e != cudaSuccess) return e;
-                attr_set = true;
-            }
-            sh_bwd_kernel<true><<<blocks, SB_THREADS, smem, stream>>>(p);
+            static PerDeviceOnce once, once_f;
+            cudaError_t e0 = factors ? ensure_dynamic_smem(sh_bwd_kernel<true, true>, 200 * 1024, once_f)
+                                     : ensure_dynamic_smem(sh_bwd_kernel<true, false>, 200 * 1024, once);
+            if (e0 != cudaSuccess) return e0;
+            if (factors) sh_bwd_kernel<true, true><<<blocks, SB_THREADS, smem, stream>>>(p);
+            else sh_bwd_kernel<true, false><<<blocks, SB_THREADS, smem, stream>>>(p);
         } else {
-            sh_bwd_kernel<false><<<blocks, SB_THREADS, 0, stream>>>(p);
+            if (factors) sh_bwd_kernel<false, true><<<blocks, SB_THREADS, 0, stream>>>(p);
+            else sh_bwd_kernel<false, false><<<blocks, SB_THREADS, 0, stream>>>(p);
         }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
     geom_bwd_kernel<<<(p.P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, stream>>>(p, has_sh ? 1 : 0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sh_outer_sum(const ShSumParams& p, cudaStream_t stream) {
+    if (p.P <= 0) return cudaSuccess;
+    const long long threads = 4ll * p.P;
+    sh_outer_sum_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

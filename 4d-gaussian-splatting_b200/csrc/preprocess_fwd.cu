@@ -414,13 +414,9 @@ cudaError_t launch_preprocess_fwd(const PreprocessFwdParams& p, cudaStream_t str
     const bool bulk = p.sh_bulk_ok && p.colors_precomp == nullptr;
     if (bulk) {
         const size_t smem = (size_t)PRE_CAP * p.sh_row_stride_floats * sizeof(float);
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(preprocess_fwd_kernel<true>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            if (e != cudaSuccess) return e;
-            attr_set = true;
-        }
+        static PerDeviceOnce once;
+        cudaError_t e = ensure_dynamic_smem(preprocess_fwd_kernel<true>, 200 * 1024, once);
+        if (e != cudaSuccess) return e;
         preprocess_fwd_kernel<true><<<blocks, PRE_THREADS, smem, stream>>>(p);
     } else {
         preprocess_fwd_kernel<false><<<blocks, PRE_THREADS, 0, stream>>>(p);

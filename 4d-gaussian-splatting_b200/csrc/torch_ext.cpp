@@ -121,9 +121,16 @@ RasterizeGaussiansCUDA(const torch::Tensor& background, const torch::Tensor& mea
                            imgBuffer, covs3D_com, out_means3D);
 }
 
-std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
-           torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
-RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Tensor& means3D,
+namespace {
+struct BackwardOut {
+    torch::Tensor dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dflows, dL_dts, dL_dscales,
+        dL_dscales_t, dL_drotations, dL_drotations_r, sh_factors;
+};
+}  // namespace
+
+// sh_factor_mode: view-parallel mode -- no dL_dsh rows, the [P,3] colour factors instead (include/fdgs.h: sh_factors)
+static BackwardOut
+backward_impl(const bool sh_factor_mode, const torch::Tensor& background, const torch::Tensor& means3D,
                                const torch::Tensor& out_means3D, const torch::Tensor& radii, const torch::Tensor& colors,
                                const torch::Tensor& flows_2d, const torch::Tensor& opacities, const torch::Tensor& ts,
                                const torch::Tensor& scales, const torch::Tensor& scales_t, const torch::Tensor& rotations,
@@ -156,7 +163,9 @@ RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Ten
     torch::Tensor dL_dmeans3D = torch::empty({P, 3}, opts);
     torch::Tensor dL_dts = torch::empty({P, 1}, opts);
     torch::Tensor dL_dcov3D = torch::empty({P, 6}, opts);
-    torch::Tensor dL_dsh = torch::empty({P, M, 3}, opts);
+    const bool factors = sh_factor_mode && M > 0;
+    torch::Tensor dL_dsh = factors ? torch::empty({0}, opts) : torch::empty({P, M, 3}, opts);
+    torch::Tensor sh_factors = factors ? torch::empty({P, 3}, opts) : torch::empty({0}, opts);
     torch::Tensor dL_dscales = torch::empty({P, 3}, opts);
     torch::Tensor dL_dscales_t = torch::empty({P, 1}, opts);
     torch::Tensor dL_drotations = torch::empty({P, 4}, opts);
@@ -190,14 +199,105 @@ RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Ten
         a.dL_dmean2D = dL_dmeans2D.data_ptr<float>(); a.dL_dconic = dL_dconic.data_ptr<float>();
         a.dL_dopacity = dL_dopacity.data_ptr<float>(); a.dL_dcolor = dL_dcolors.data_ptr<float>();
         a.dL_dflows = dL_dflows.data_ptr<float>(); a.dL_dmean3D = dL_dmeans3D.data_ptr<float>();
-        a.dL_dcov3D = dL_dcov3D.data_ptr<float>(); a.dL_dsh = M > 0 ? dL_dsh.data_ptr<float>() : nullptr;
+        a.dL_dcov3D = dL_dcov3D.data_ptr<float>(); a.dL_dsh = (M > 0 && !factors) ? dL_dsh.data_ptr<float>() : nullptr;
+        a.sh_factors = factors ? sh_factors.data_ptr<float>() : nullptr;
         a.dL_dts = dL_dts.data_ptr<float>(); a.dL_dscale = dL_dscales.data_ptr<float>();
         a.dL_dscale_t = dL_dscales_t.data_ptr<float>(); a.dL_drot = dL_drotations.data_ptr<float>();
         a.dL_drot_r = dL_drotations_r.data_ptr<float>();
         check(fdgs_backward(&a, (void*)stream), "backward");
     }
-    return std::make_tuple(dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dflows, dL_dts,
-                           dL_dscales, dL_dscales_t, dL_drotations, dL_drotations_r);
+    return BackwardOut{dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dflows, dL_dts,
+                       dL_dscales, dL_dscales_t, dL_drotations, dL_drotations_r, sh_factors};
+}
+
+#define FDGS_BWD_PARAMS                                                                                                \
+    const torch::Tensor &background, const torch::Tensor &means3D, const torch::Tensor &out_means3D,                  \
+        const torch::Tensor &radii, const torch::Tensor &colors, const torch::Tensor &flows_2d,                        \
+        const torch::Tensor &opacities, const torch::Tensor &ts, const torch::Tensor &scales,                          \
+        const torch::Tensor &scales_t, const torch::Tensor &rotations, const torch::Tensor &rotations_r,               \
+        const float scale_modifier, const torch::Tensor &cov3D_precomp, const float prefilter_var,                     \
+        const torch::Tensor &viewmatrix, const torch::Tensor &projmatrix, const float tan_fovx, const float tan_fovy,  \
+        const torch::Tensor &dL_dout_color, const torch::Tensor &dL_dout_depth, const torch::Tensor &dL_dout_mask,     \
+        const torch::Tensor &dL_dout_flow, const torch::Tensor &sh, const int degree, const int degree_t,              \
+        const torch::Tensor &campos, const float timestamp, const float time_duration, const bool rot_4d,              \
+        const int gaussian_dim, const bool force_sh_3d, const torch::Tensor &geomBuffer, const int R,                  \
+        const torch::Tensor &binningBuffer, const torch::Tensor &imageBuffer, const bool debug
+#define FDGS_BWD_ARGS                                                                                                  \
+    background, means3D, out_means3D, radii, colors, flows_2d, opacities, ts, scales, scales_t, rotations, rotations_r, \
+        scale_modifier, cov3D_precomp, prefilter_var, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color,       \
+        dL_dout_depth, dL_dout_mask, dL_dout_flow, sh, degree, degree_t, campos, timestamp, time_duration, rot_4d,     \
+        gaussian_dim, force_sh_3d, geomBuffer, R, binningBuffer, imageBuffer, debug
+
+// the reference's entry point: 37 positional arguments, 12 gradients (rasterize_points.h:51-89)
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
+           torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
+RasterizeGaussiansBackwardCUDA(FDGS_BWD_PARAMS) {
+    BackwardOut o = backward_impl(false, FDGS_BWD_ARGS);
+    return std::make_tuple(o.dL_dmeans2D, o.dL_dcolors, o.dL_dopacity, o.dL_dmeans3D, o.dL_dcov3D, o.dL_dsh, o.dL_dflows,
+                           o.dL_dts, o.dL_dscales, o.dL_dscales_t, o.dL_drotations, o.dL_drotations_r);
+}
+
+// view-parallel variant: same arguments; dL_dsh comes back EMPTY and a 13th tensor holds the [P,3] colour factors
+std::vector<torch::Tensor> RasterizeGaussiansBackwardFactors(FDGS_BWD_PARAMS) {
+    BackwardOut o = backward_impl(true, FDGS_BWD_ARGS);
+    return {o.dL_dmeans2D, o.dL_dcolors, o.dL_dopacity, o.dL_dmeans3D, o.dL_dcov3D, o.dL_dsh, o.dL_dflows,
+            o.dL_dts, o.dL_dscales, o.dL_dscales_t, o.dL_drotations, o.dL_drotations_r, o.sh_factors};
+}
+
+// rebuild + sum the dL_dsh rows of all views from the gathered colour factors (include/fdgs.h: fdgs_sh_outer_sum)
+void ShOuterSum(const torch::Tensor& table, const int64_t view_stride, const int64_t meta_off, const int64_t V,
+                const int64_t K, const torch::Tensor& slot_of, const torch::Tensor& means3D, const torch::Tensor& ts,
+                const torch::Tensor& scales, const torch::Tensor& scales_t, const torch::Tensor& rotations,
+                const torch::Tensor& rotations_r, const double scale_modifier, const double time_duration,
+                const bool rot_4d, const int64_t gaussian_dim, const bool force_sh_3d, const int64_t D, const int64_t D_t,
+                std::vector<torch::Tensor> outs, const bool accumulate) {
+    TORCH_CHECK(outs.size() == 1 || outs.size() == 2, "fdgs: one or two output tensors");
+    TORCH_CHECK(slot_of.is_cuda() && slot_of.scalar_type() == torch::kInt32 && slot_of.is_contiguous(), "fdgs: slot_of must be int32 CUDA");
+    const int P = means3D.size(0);
+    for (auto& o : outs)
+        TORCH_CHECK(o.is_cuda() && o.scalar_type() == torch::kFloat32 && o.is_contiguous() && o.dim() == 3 && o.size(0) == P &&
+                    o.size(2) == 3, "fdgs: outputs must be contiguous float32 [P, m, 3] CUDA tensors");
+    const c10::cuda::CUDAGuard guard(means3D.device());
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream().stream();
+    const auto m_c = contig(means3D), ts_c = contig(ts), sc_c = contig(scales), sct_c = contig(scales_t),
+               rot_c = contig(rotations), rotr_c = contig(rotations_r), tb_c = contig(table);
+    fdgs_sh_sum_args a;
+    memset(&a, 0, sizeof(a));
+    a.P = P; a.V = (int)V; a.K = (int)K; a.table = fptr(tb_c); a.view_stride = view_stride; a.meta_off = meta_off;
+    a.slot_of = slot_of.data_ptr<int>(); a.means3D = fptr(m_c); a.ts = fptr(ts_c); a.scales = fptr(sc_c);
+    a.scales_t = fptr(sct_c); a.rotations = fptr(rot_c); a.rotations_r = fptr(rotr_c);
+    a.scale_modifier = (float)scale_modifier; a.time_duration = (float)time_duration; a.rot_4d = rot_4d;
+    a.gaussian_dim = (int)gaussian_dim; a.force_sh_3d = force_sh_3d; a.D = (int)D; a.D_t = (int)D_t;
+    a.m0 = (int)outs[0].size(1);
+    a.M = a.m0 + (outs.size() == 2 ? (int)outs[1].size(1) : 0);
+    a.out0 = outs[0].data_ptr<float>();
+    a.out1 = outs.size() == 2 ? outs[1].data_ptr<float>() : nullptr;
+    a.accumulate = accumulate;
+    if (V > 0) TORCH_CHECK(tb_c.numel() >= V * view_stride, "fdgs: factor table too small");
+    check(fdgs_sh_outer_sum(&a, (void*)stream), "sh_outer_sum");
+}
+
+// 1-element int32 tensor, non-zero if a row of `tensors` outside radii > 0 is not all-zero (sparse-exchange guard)
+torch::Tensor CheckRowsZero(std::vector<torch::Tensor> tensors, const torch::Tensor& radii) {
+    TORCH_CHECK((int)tensors.size() <= FDGS_MAX_PACK, "fdgs: too many tensors");
+    TORCH_CHECK(radii.is_cuda() && radii.scalar_type() == torch::kInt32 && radii.is_contiguous(), "fdgs: radii must be int32 CUDA");
+    torch::Tensor flag = torch::zeros({1}, radii.options());
+    const long long P = radii.numel();
+    if (tensors.empty() || P == 0) return flag;
+    std::vector<const float*> ptr;
+    std::vector<int> widths;
+    for (const auto& t : tensors) {
+        TORCH_CHECK(t.is_cuda() && t.scalar_type() == torch::kFloat32 && t.is_contiguous() && t.size(0) == P,
+                    "fdgs: gradient tensors must be contiguous float32 CUDA tensors with P rows");
+        ptr.push_back(t.data_ptr<float>());
+        widths.push_back((int)(t.numel() / P));
+    }
+    const c10::cuda::CUDAGuard guard(radii.device());
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream().stream();
+    check(fdgs_check_rows_zero((int)ptr.size(), ptr.data(), widths.data(), P, radii.data_ptr<int>(), flag.data_ptr<int>(),
+                               (void*)stream),
+          "check_rows_zero");
+    return flag;
 }
 
 torch::Tensor markVisible(torch::Tensor& means3D, torch::Tensor& viewmatrix, torch::Tensor& projmatrix) {
@@ -310,6 +410,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("unpack_rows", &UnpackRows);
     m.def("rasterize_gaussians", &RasterizeGaussiansCUDA);
     m.def("rasterize_gaussians_backward", &RasterizeGaussiansBackwardCUDA);
+    m.def("rasterize_gaussians_backward_factors", &RasterizeGaussiansBackwardFactors);
+    m.def("sh_outer_sum", &ShOuterSum);
+    m.def("check_rows_zero", &CheckRowsZero);
     m.def("mark_visible", &markVisible);
     m.def("debug_export_geom", &DebugExportGeom);
     m.def("debug_export_binning", &DebugExportBinning);

@@ -66,6 +66,19 @@ def make_camera(W, H, timestamp=0.5, focal_scale=0.54, negative_fov=False, R=Non
     return Camera(W, H, fovx, fovy, view, full, center, timestamp)
 
 
+def pose_from_euler(yaw_deg, pitch_deg, roll_deg, ex, ey, ez):
+    """Camera-to-world rotation R (columns = camera axes) from yaw (about y), pitch (about x), roll (about z), and
+    the world-to-camera translation T = -R^T eye of a camera at `eye` -- the (R, T) pair make_camera() takes
+    (reference convention: scene/cameras.py:59-71 with utils/graphics_utils.py:39-55 getWorld2View2)."""
+    y, p, r = (math.radians(a) for a in (yaw_deg, pitch_deg, roll_deg))
+    Ry = torch.tensor([[math.cos(y), 0.0, math.sin(y)], [0.0, 1.0, 0.0], [-math.sin(y), 0.0, math.cos(y)]])
+    Rx = torch.tensor([[1.0, 0.0, 0.0], [0.0, math.cos(p), -math.sin(p)], [0.0, math.sin(p), math.cos(p)]])
+    Rz = torch.tensor([[math.cos(r), -math.sin(r), 0.0], [math.sin(r), math.cos(r), 0.0], [0.0, 0.0, 1.0]])
+    R = (Ry @ Rx @ Rz).contiguous()
+    eye = torch.tensor([ex, ey, ez])
+    return R, -(R.t() @ eye)
+
+
 @dataclass
 class Scene:
     """Activated (post exp/normalize/sigmoid) Gaussian parameters, i.e. the rasterizer's inputs."""
@@ -118,7 +131,13 @@ def make_scene(P, cam: Camera, seed, M=48, sh_degree=3, sh_degree_t=2, sigma_px=
     z = zmin + (zmax - zmin) * u(P)
     x = (2 * u(P) - 1) * frustum * tanx * z
     y = (2 * u(P) - 1) * frustum * tany * z
-    means = torch.stack([x, y, z], dim=1).contiguous()
+    means = torch.stack([x, y, z], dim=1)
+    # the points are drawn in the camera frame; a posed camera sees them through world = R (p_cam - T)
+    w2c = cam.world_view_transform.t()            # [4,4] row-major world-to-camera
+    Rc, Tc = w2c[:3, :3], w2c[:3, 3]              # p_cam = Rc p_world + Tc
+    if not (torch.equal(Rc, torch.eye(3)) and torch.equal(Tc, torch.zeros(3))):
+        means = (means - Tc) @ Rc                 # = Rc^T (p_cam - Tc), row-vector form
+    means = means.contiguous()
     ts = u(P, 1) * time_duration
     # ~sigma_px pixels on screen: focal ~= W / (2 tanx)
     px_world = (2 * tanx / cam.image_width) * z

@@ -113,12 +113,25 @@ class _RasterizeGaussians(torch.autograd.Function):
                 s.projmatrix, s.tanfovx, s.tanfovy, grad_out_color, grad_depth, grad_alpha, grad_flow, sh,
                 s.sh_degree, s.sh_degree_t, s.campos, s.timestamp, s.time_duration, s.rot_4d, s.gaussian_dim,
                 s.force_sh_3d, geom_buf, ctx.num_rendered, binning_buf, img_buf, s.debug)
-        (g_means2D, g_colors, g_opacities, g_means3D, g_cov3D, g_sh, g_flows, g_ts, g_scales, g_scales_t,
-         g_rot, g_rot_r) = _invoke(_C.rasterize_gaussians_backward, args, s.debug, "snapshot_bw.dump")
+        # View-parallel step (fdgs/dist.py, multi-GPU): the dense dL_dsh of this view is not produced; the backward
+        # emits the [P,3] colour factor of its rank-one rows and the step rebuilds / sums the rows of all views after
+        # the exchange.  No reference counterpart (its views are sequential on one GPU, train.py:104-166).
+        from fdgs.dist import ViewParallelStep
+        step = ViewParallelStep.current()
+        if step is not None and step.wants_factors(sh, cov3Ds_precomp) and ctx.needs_input_grad[2]:
+            out = _invoke(_C.rasterize_gaussians_backward_factors, args, s.debug, "snapshot_bw.dump")
+            (g_means2D, g_colors, g_opacities, g_means3D, g_cov3D, _no_sh, g_flows, g_ts, g_scales, g_scales_t,
+             g_rot, g_rot_r, factors) = out
+            step.record_view(factors, s, dict(means3D=means3D, ts=ts, scales=scales, scales_t=scales_t,
+                                              rotations=rotations, rotations_r=rotations_r))
+            g_sh = None
+        else:
+            (g_means2D, g_colors, g_opacities, g_means3D, g_cov3D, g_sh, g_flows, g_ts, g_scales, g_scales_t,
+             g_rot, g_rot_r) = _invoke(_C.rasterize_gaussians_backward, args, s.debug, "snapshot_bw.dump")
 
         def for_input(grad, inp):
             # inputs passed as the empty "not provided" placeholder take no gradient
-            return grad if inp.numel() > 0 else None
+            return grad if (inp.numel() > 0 and grad is not None) else None
 
         # one entry per forward input (reference: :208-223); prefilter_var / settings get None
         return (g_means3D, g_means2D, for_input(g_sh, sh), for_input(g_colors, colors_precomp),

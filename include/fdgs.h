@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define FDGS_VERSION 1
+#define FDGS_VERSION 2
 
 /* status codes */
 #define FDGS_OK 0
@@ -161,6 +161,11 @@ typedef struct fdgs_backward_args {
     float* dL_dscale_t;    /* [P]     overwritten                              */
     float* dL_drot;        /* [P,4]   overwritten                              */
     float* dL_drot_r;      /* [P,4]   overwritten                              */
+    /* View-parallel mode (version 2; multi-GPU, see fdgs_sh_outer_sum below): when `sh_factors` is non-NULL and
+     * dL_dsh is NULL the 12*M-byte dL_dsh rows are NOT written; instead sh_factors[P,3] receives the clamp-masked
+     * colour gradient of every Gaussian (zeros where this view did not render it) -- the only view-dependent factor
+     * of the rank-one dL_dsh row.  The direction / time terms of the SH backward still go to dL_dmean3D / dL_dts. */
+    float* sh_factors;     /* [P,3]   overwritten, or NULL                     */
 } fdgs_backward_args;
 
 /* Library / build identification. */
@@ -202,6 +207,41 @@ int fdgs_pack_rows(int n, const float* const* tensors, const int* widths, const 
                    const long long* idx, long long K, float* flat, void* stream);
 int fdgs_unpack_rows(int n, float* const* tensors, const int* widths, const long long* block_off,
                      const long long* idx, long long K, const float* flat, void* stream);
+
+/* View-parallel SH gradient (multi-GPU; new -- the reference sums the dL_dsh of sequential views in autograd,
+ * train.py:104-166).  After the colour factors of all V views of a step have been all-gathered for the K Gaussians
+ * of the union (table = V blocks of `view_stride` floats: K rows of 3 floats, then at `meta_off` the view's
+ * timestamp and camera position), rebuilds every view's rank-one dL_dsh row from the replicated Gaussian
+ * parameters and sums them in view order: out[i] = sum_v w(dir_v(i), t_v) x factors_v[slot_of[i]], zeros for
+ * slot_of[i] < 0.  Bit-identical to accumulating the views' dL_dsh tensors one after the other.  The row may be
+ * split over two tensors (out0 = first m0 coefficients, out1 = the rest; out1 NULL and m0 = M for one tensor). */
+typedef struct fdgs_sh_sum_args {
+    int P, V, K;
+    const float* table;
+    long long view_stride;
+    long long meta_off;
+    const int* slot_of;           /* [P]                                       */
+    const float* means3D;         /* [P,3] the rasterizer's inputs (replicated) */
+    const float* ts;              /* [P] or NULL                               */
+    const float* scales;          /* [P,3] (needed when rot_4d)                */
+    const float* scales_t;        /* [P]                                       */
+    const float* rotations;       /* [P,4]                                     */
+    const float* rotations_r;     /* [P,4]                                     */
+    float scale_modifier;
+    float time_duration;
+    int rot_4d, gaussian_dim, force_sh_3d;
+    int D, D_t, M;
+    float* out0;
+    int m0;
+    float* out1;
+    int accumulate;
+} fdgs_sh_sum_args;
+int fdgs_sh_outer_sum(const fdgs_sh_sum_args* args, void* stream);
+
+/* flag[0] |= 1 if a row r with radii[r] <= 0 of any of the n tensors ([P, widths[i]], device) holds a non-zero
+ * element: the guard of the sparse (union-rows-only) gradient exchange.  `tensors` / `widths` are HOST arrays. */
+int fdgs_check_rows_zero(int n, const float* const* tensors, const int* widths, long long P, const int* radii,
+                         int* flag, void* stream);
 
 /* Test/diagnostic hooks (used by tests/ and bench.py only): copy private
  * per-Gaussian / per-instance state out of the scratch buffers into plain

@@ -26,7 +26,26 @@ CONFIGS = {
     "deg1": dict(P=3000, W=160, H=112, seed=82, sh_degree=1, sh_degree_t=0, M=48),
     "m16": dict(P=3000, W=160, H=112, seed=83, sh_degree=3, sh_degree_t=0, M=16),
     "prefilter": dict(P=3000, W=160, H=112, seed=84, prefilter_var=0.01),
+    # --- inputs the first golden set never exercised ---
+    # N3V-style time axis: duration 10, timestamps off 0.5 -> the double-precision Fourier angle of the 4D SH
+    "dur10": dict(P=3000, W=160, H=112, seed=85, time_duration=10.0, timestamp=3.7, scale_t_mean=1.2),
+    # densification previews render with scaling_modifier != 1 (reference: gaussian_renderer/__init__.py:19,39)
+    "smod05": dict(P=3000, W=160, H=112, seed=86, scale_modifier=0.5),
+    "smod2": dict(P=3000, W=160, H=112, seed=87, scale_modifier=2.0),
+    # rotated + translated camera: non-identity view matrix, campos != 0 (every SH direction, the EWA Jacobian)
+    "rotcam": dict(P=3000, W=160, H=112, seed=88, pose=(25.0, -10.0, 5.0, 0.7, -0.4, 1.2), flow=True, bg=(0.2, 0.1, 0.4)),
+    # flame_steak shape in miniature: duration [0,10], negative FoV (quirk 7), posed camera, all at once
+    "n3v": dict(P=3000, W=160, H=112, seed=89, time_duration=10.0, timestamp=6.3, scale_t_mean=1.2, negative_fov=True,
+                pose=(-15.0, 8.0, -3.0, -0.5, 0.3, 0.8)),
+    "deg1m4": dict(P=3000, W=160, H=112, seed=90, sh_degree=1, sh_degree_t=0, M=4),   # row shorter than a 16-block
     "mid": dict(P=100000, W=640, H=480, seed=1236),
+    "mid_rotcam": dict(P=100000, W=640, H=480, seed=1238, pose=(25.0, -10.0, 5.0, 0.7, -0.4, 1.2)),
+    "mid_dur10": dict(P=100000, W=640, H=480, seed=1239, time_duration=10.0, timestamp=3.7, scale_t_mean=1.2),
+    "mid_smod2": dict(P=100000, W=640, H=480, seed=1240, scale_modifier=2.0),
+    "q250k": dict(P=250000, W=478, H=358, seed=1237),          # 1/8-scale replica of cfg3 (same density)
+    # BASELINE config 5 (N3V flame_steak shape): 300k Gaussians, duration [0,10], 1352x1014, posed N3V-style camera
+    "cfg5": dict(P=300000, W=1352, H=1014, seed=1241, time_duration=10.0, timestamp=4.3, scale_t_mean=1.2,
+                 pose=(10.0, -5.0, 0.0, 0.3, -0.2, 0.5)),
     "cfg2": dict(P=500000, W=1352, H=1014, seed=1236),
     "cfg3": dict(P=2000000, W=1352, H=1014, seed=1237),
 }
@@ -40,13 +59,18 @@ ORACLE_GRAD_KEYS = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "
 
 def build(name_or_cfg, device="cpu"):
     cfg = CONFIGS[name_or_cfg] if isinstance(name_or_cfg, str) else name_or_cfg
-    cam = synth.make_camera(cfg["W"], cfg["H"], negative_fov=cfg.get("negative_fov", False))
+    R = T = None
+    if cfg.get("pose") is not None:
+        R, T = synth.pose_from_euler(*cfg["pose"])
+    cam = synth.make_camera(cfg["W"], cfg["H"], timestamp=cfg.get("timestamp", 0.5),
+                            negative_fov=cfg.get("negative_fov", False), R=R, T=T)
     sc = synth.make_scene(cfg["P"], cam, cfg["seed"], flow=cfg.get("flow", False), M=cfg.get("M", 48),
                           sh_degree=cfg.get("sh_degree", 3), sh_degree_t=cfg.get("sh_degree_t", 2),
                           rot_4d=cfg.get("rot_4d", True), gaussian_dim=cfg.get("gaussian_dim", 4),
-                          force_sh_3d=cfg.get("force_sh_3d", False))
+                          force_sh_3d=cfg.get("force_sh_3d", False), time_duration=cfg.get("time_duration", 1.0),
+                          scale_t_mean=cfg.get("scale_t_mean", 0.15))
     bg = torch.tensor(cfg.get("bg", (0.0, 0.0, 0.0)), dtype=torch.float32)
-    st = synth.raster_settings(cam, sc, bg=bg, device=device)
+    st = synth.raster_settings(cam, sc, bg=bg, scale_modifier=cfg.get("scale_modifier", 1.0), device=device)
     return cfg, cam, sc.to(device), st
 
 

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(repo_root):
     for s in _header_symbols(repo_root):
         assert hasattr(lib, s), "libfdgs.so does not export %s" % s
     assert set(_header_symbols(repo_root)) == set(fdgs.ABI_SYMBOLS)
-    assert lib.fdgs_version() == 1
+    assert lib.fdgs_version() == 2
     assert lib.fdgs_last_error() == b""
 
 

@@ -125,3 +125,126 @@ def test_sparse_union_allreduce_equals_dense():
         same, frac, dense_ok = out[r]
         assert same and dense_ok
         assert 0.3 < frac < 0.6
+
+
+# ---------------------------------------------------------------------------------------------------
+# SH colour-factor exchange (ViewParallelStep): the host logic -- union / slots / table layout / view order --
+# on gloo, with the CUDA reconstruction kernel replaced by its PyTorch reference (tests/sh_outer_ref.py).
+# ---------------------------------------------------------------------------------------------------
+class _S:
+    """the per-step constants the step reads from a view's raster settings"""
+    def __init__(self, timestamp, campos):
+        self.timestamp, self.campos = timestamp, campos
+        self.scale_modifier, self.time_duration, self.rot_4d, self.gaussian_dim, self.force_sh_3d = 1.0, 1.0, True, 4, False
+        self.sh_degree, self.sh_degree_t = 3, 2
+
+
+def _factor_scene(P):
+    g = torch.Generator().manual_seed(5)
+    n = lambda *s: torch.randn(*s, generator=g)
+    inputs = dict(means3D=n(P, 3) + torch.tensor([0.0, 0.0, 5.0]), ts=torch.rand(P, 1, generator=g),
+                  scales=0.05 * torch.rand(P, 3, generator=g) + 0.01, scales_t=0.2 * torch.rand(P, 1, generator=g) + 0.1,
+                  rotations=torch.nn.functional.normalize(n(P, 4), dim=1),
+                  rotations_r=torch.nn.functional.normalize(n(P, 4), dim=1))
+    return inputs
+
+
+def _factor_view(P, v):
+    g = torch.Generator().manual_seed(900 + v)
+    vis = torch.rand(P, generator=g) < 0.12
+    radii = (torch.randint(1, 40, (P,), generator=g) * vis).to(torch.int32)
+    factors = torch.randn(P, 3, generator=g) * vis[:, None]
+    geo = torch.randn(P, 3, generator=g) * vis[:, None]
+    screen = torch.randn(P, 3, generator=g) * vis[:, None]
+    return factors, radii, geo, screen, _S(0.1 + 0.2 * v, torch.tensor([0.1 * v, -0.05 * v, 0.02 * v]))
+
+
+def _outer_ref_fn(inputs):
+    import sh_outer_ref
+
+    def fn(table, stride, meta_off, V, K, slot_of, outs, views):
+        full = sh_outer_ref.sh_outer_sum_ref(table, stride, meta_off, V, K, slot_of, inputs["means3D"], inputs["ts"],
+                                             inputs["scales"], inputs["scales_t"], inputs["rotations"],
+                                             inputs["rotations_r"], 1.0, 1.0, True, 4, False, 3, 2, 48)
+        off = 0
+        for o in outs:
+            o.copy_(full[:, off:off + o.shape[1]])
+            off += o.shape[1]
+    return fn
+
+
+def _run_factor_step(P, view_ids, group_world, split):
+    inputs = _factor_scene(P)
+    xyz = torch.zeros(P, 3, requires_grad=True)
+    shs = [torch.zeros(P, 1, 3, requires_grad=True), torch.zeros(P, 47, 3, requires_grad=True)] if split else \
+        [torch.zeros(P, 48, 3, requires_grad=True)]
+    step = fdist.ViewParallelStep(P, "cpu", outer_sum_fn=_outer_ref_fn(inputs))
+    xyz.grad = torch.zeros(P, 3)
+    for v in view_ids:
+        factors, radii, geo, screen, S = _factor_view(P, v)
+        xyz.grad += geo
+        step.record_view(factors, S, inputs)
+        step.add_view_stats(screen, radii)
+    st = step.finish([xyz], shs, views_per_rank=None)
+    return xyz.grad, torch.cat([p.grad for p in shs], 1), st, step.info
+
+
+def _factor_worker(rank, world, port, P, num_views, split, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        gx, gsh, st, info = _run_factor_step(P, fdist.shard_views(num_views, rank, world), world, split)
+        out[rank] = (gx.clone(), gsh.clone(), st.grad_norm_sum.clone(), st.visibility_count.clone(), st.max_radii.clone(), info)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("num_views,split", [(2, False), (4, True), (3, False)])
+def test_sh_factor_exchange_matches_single_process(num_views, split):
+    """2 ranks x (views / 2) == 1 process x all views: geometry rows, statistics and the rebuilt SH rows, including
+    an uneven view split (3 views: the padded zero view of the rank with fewer views contributes nothing)."""
+    P, world = 301, 2
+    ref_x, ref_sh, ref_st, _ = _run_factor_step(P, list(range(num_views)), 1, split)
+    assert float(ref_sh.abs().sum()) > 0
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_factor_worker, args=(world, _free_port(), P, num_views, split, out), nprocs=world, join=True)
+    assert len(out) == world
+    for r in range(world):
+        gx, gsh, gn, vc, mr, info = out[r]
+        assert torch.allclose(gx, ref_x, rtol=1e-6, atol=1e-6)
+        assert torch.equal(gsh, ref_sh)            # same views in the same order through the same arithmetic
+        assert torch.allclose(gn, ref_st.grad_norm_sum, rtol=1e-6, atol=1e-6)
+        assert torch.equal(vc, ref_st.visibility_count) and torch.equal(mr, ref_st.max_radii)
+        assert info["geometry_path"] == "rows" and info["views_total"] == 2 * ((num_views + 1) // 2)
+    assert torch.equal(out[0][1], out[1][1])       # replicas stay bit-identical
+
+
+def _dense_guard_worker(rank, world, port, P, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(3 + rank)
+        vis = torch.rand(P, generator=g) < 0.3
+        radii = vis.to(torch.int32) * 5
+        dist.all_reduce(radii, op=dist.ReduceOp.MAX)
+        # a gradient that is NOT confined to the rendered Gaussians (e.g. a rigidity loss over all of them)
+        full = torch.randn(P, 3, generator=g)
+        want = full.clone()
+        dist.all_reduce(want)
+        fdist.allreduce_gradients([full], union_radii=radii)
+        out[rank] = torch.equal(full, want)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sparse_exchange_detects_non_rasterizer_gradients():
+    """rows outside the union are only zero for rasterizer gradients; a loss over ALL Gaussians must not be
+    silently under-reduced -- the device-side guard routes the step to the dense all-reduce."""
+    world, P = 2, 500
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_dense_guard_worker, args=(world, _free_port(), P, out), nprocs=world, join=True)
+    assert all(out[r] for r in range(world))
