@@ -929,3 +929,14 @@ int oracle_num_threads(void) {
     return 1;
 #endif
 }
+
+/* n <= 0 restores the default (all host cores); used by bench.py to time cfg1 with one thread and with all */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    extern void omp_set_num_threads(int);
+    extern int omp_get_num_procs(void);
+    omp_set_num_threads(n > 0 ? n : omp_get_num_procs());
+#else
+    (void)n;
+#endif
+}

@@ -191,6 +191,11 @@ def num_threads():
     return int(lib().oracle_num_threads())
 
 
+def set_num_threads(n):
+    """n <= 0: back to all host cores"""
+    lib().oracle_set_num_threads(int(n))
+
+
 # ---- the compiled, unmodified reference (oracle/_ref) ----------------------------------------------
 _ref = None
 

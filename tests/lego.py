@@ -1,0 +1,100 @@
+"""BASELINE config 4 ("lego" shape) in miniature: the optimisation loop of the reference's train.py:84-249 over a
+synthetic D-NeRF-like scene (100k points in (-1.3, 1.3)^3, 800x800, batch of 2 views, hyper-parameters of
+configs/dnerf/lego.yaml:36-44), runnable through this package's render() or through the compiled reference
+rasterizer.  Shared by tests/test_gpu_parity.py (loss curves must track) and bench.py --workload cfg4 (it/s).
+TEST / BENCH INFRASTRUCTURE."""
+import numpy as np
+import torch
+
+DEV = "cuda:0"
+
+
+class _Pipe:
+    convert_SHs_python = False
+    compute_cov3D_python = False
+    debug = False
+    env_map_res = 0
+
+
+def lego_setup(P, W, H, seed):
+    import math
+    from fdgs import synth
+    g = torch.Generator().manual_seed(seed)
+    cams = []
+    for k in range(4):   # cameras on a circle of radius 4 looking at the origin, different timestamps
+        ang = 2 * math.pi * k / 4 + 0.3
+        eye = torch.tensor([4 * math.cos(ang), 0.6 * (k - 1.5), 4 * math.sin(ang)])
+        fwd = torch.nn.functional.normalize(-eye, dim=0)
+        right = torch.nn.functional.normalize(torch.linalg.cross(torch.tensor([0.0, 1.0, 0.0]), fwd), dim=0)
+        up = torch.linalg.cross(fwd, right)
+        R = torch.stack([right, up, fwd], 1)              # camera-to-world rotation (columns = camera axes)
+        T = -(R.t() @ eye)
+        cams.append(synth.make_camera(W, H, timestamp=0.2 + 0.2 * k, focal_scale=1.1, R=R, T=T))
+
+    def params(scale):
+        u = lambda *s: torch.rand(*s, generator=g)
+        n = lambda *s: torch.randn(*s, generator=g)
+        return dict(xyz=(u(P, 3) * 2.6 - 1.3), t=u(P, 1), log_s=torch.log(0.012 * scale * (0.5 + u(P, 3))),
+                    log_st=torch.full((P, 1), math.log(math.sqrt(1.0 / 5))) + 0.1 * n(P, 1),     # gaussian_model.py:280-281
+                    rot=torch.nn.functional.normalize(n(P, 4), dim=1), rot_r=torch.nn.functional.normalize(n(P, 4), dim=1),
+                    op=torch.logit(torch.full((P, 1), 0.1)) + 0.5 * n(P, 1),                      # gaussian_model.py:286
+                    sh=torch.cat([(u(P, 1, 3) - 0.5) / 0.28209479177387814, 0.02 * n(P, 47, 3)], 1))
+    return cams, params(1.0), params(1.3)
+
+
+class LegoModel:
+    """The reference's GaussianModel getters (scene/gaussian_model.py:179-219) over raw parameters."""
+
+    def __init__(self, raw):
+        self.raw = raw
+        self.active_sh_degree, self.active_sh_degree_t = 3, 2
+        self.time_duration = [0.0, 1.0]
+        self.rot_4d, self.gaussian_dim, self.force_sh_3d, self.prefilter_var = True, 4, False, -1.0
+        self.get_max_sh_channels = 48
+
+    get_xyz = property(lambda s: s.raw["xyz"])
+    get_t = property(lambda s: s.raw["t"])
+    get_scaling = property(lambda s: torch.exp(s.raw["log_s"]))
+    get_scaling_t = property(lambda s: torch.exp(s.raw["log_st"]))
+    get_rotation = property(lambda s: torch.nn.functional.normalize(s.raw["rot"]))
+    get_rotation_r = property(lambda s: torch.nn.functional.normalize(s.raw["rot_r"]))
+    get_opacity = property(lambda s: torch.sigmoid(s.raw["op"]))
+    get_features = property(lambda s: s.raw["sh"])
+
+
+def lego_render(model, cam, impl):
+    if impl == "ours":
+        from gaussian_renderer import render
+        return render(cam, model, _Pipe(), torch.zeros(3, device=DEV))["render"]
+    import ref_api
+    from fdgs import synth
+    m = model
+    dummy = type("S", (), dict(sh_degree=3, sh_degree_t=2, time_duration=1.0, rot_4d=True, gaussian_dim=4, force_sh_3d=False))
+    st = synth.raster_settings(cam, dummy, device=DEV)
+    means2D = torch.zeros_like(m.get_xyz, requires_grad=True)
+    out = ref_api.rasterize(st, m.get_xyz, means2D, m.get_opacity, m.get_features, torch.zeros(m.get_xyz.shape[0], 2, device=DEV),
+                            m.get_t, m.get_scaling, m.get_scaling_t, m.get_rotation, m.get_rotation_r)
+    return out[0]
+
+
+def make_optimizer(raw):
+    """Adam over the raw parameters with the learning rates of configs/dnerf/lego.yaml:36-44 (eps 1e-15 as
+    scene/gaussian_model.py:331-357)."""
+    return torch.optim.Adam([{"params": [raw["xyz"]], "lr": 1.6e-4}, {"params": [raw["t"]], "lr": 1.6e-4},
+                             {"params": [raw["sh"]], "lr": 2.5e-3}, {"params": [raw["op"]], "lr": 5e-2},
+                             {"params": [raw["log_s"], raw["log_st"]], "lr": 5e-3},
+                             {"params": [raw["rot"], raw["rot_r"]], "lr": 1e-3}], eps=1e-15)
+
+
+def train_iteration(model, opt, cams, gts, it, batch, impl, device=DEV):
+    """One iteration of train.py's loop: `batch` sequential views, L1 loss / batch, one Adam step."""
+    total = torch.zeros((), device=device)
+    for b in range(batch):
+        k = (it * batch + b) % len(cams)
+        img = lego_render(model, cams[k], "ours" if impl == "ours" else "ref")
+        loss = (img - gts[k]).abs().mean() / batch
+        loss.backward()
+        total += loss.detach()
+    opt.step()
+    opt.zero_grad(set_to_none=True)
+    return total

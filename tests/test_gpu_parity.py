@@ -526,65 +526,7 @@ def test_pack_unpack_rows_exchange_kernels(C):
 # the optimisation loop of train.py:84-249 in miniature, once through this package's render(), once through the
 # compiled reference rasterizer, same seeds -- the two loss curves must track each other.
 # ---------------------------------------------------------------------------------------------------
-def _lego_setup(P, W, H, seed):
-    import math
-    from fdgs import synth
-    g = torch.Generator().manual_seed(seed)
-    cams = []
-    for k in range(4):   # cameras on a circle of radius 4 looking at the origin, different timestamps
-        ang = 2 * math.pi * k / 4 + 0.3
-        eye = torch.tensor([4 * math.cos(ang), 0.6 * (k - 1.5), 4 * math.sin(ang)])
-        fwd = torch.nn.functional.normalize(-eye, dim=0)
-        right = torch.nn.functional.normalize(torch.linalg.cross(torch.tensor([0.0, 1.0, 0.0]), fwd), dim=0)
-        up = torch.linalg.cross(fwd, right)
-        R = torch.stack([right, up, fwd], 1)              # camera-to-world rotation (columns = camera axes)
-        T = -(R.t() @ eye)
-        cams.append(synth.make_camera(W, H, timestamp=0.2 + 0.2 * k, focal_scale=1.1, R=R, T=T))
-
-    def params(scale):
-        u = lambda *s: torch.rand(*s, generator=g)
-        n = lambda *s: torch.randn(*s, generator=g)
-        return dict(xyz=(u(P, 3) * 2.6 - 1.3), t=u(P, 1), log_s=torch.log(0.012 * scale * (0.5 + u(P, 3))),
-                    log_st=torch.full((P, 1), math.log(math.sqrt(1.0 / 5))) + 0.1 * n(P, 1),     # gaussian_model.py:280-281
-                    rot=torch.nn.functional.normalize(n(P, 4), dim=1), rot_r=torch.nn.functional.normalize(n(P, 4), dim=1),
-                    op=torch.logit(torch.full((P, 1), 0.1)) + 0.5 * n(P, 1),                      # gaussian_model.py:286
-                    sh=torch.cat([(u(P, 1, 3) - 0.5) / 0.28209479177387814, 0.02 * n(P, 47, 3)], 1))
-    return cams, params(1.0), params(1.3)
-
-
-class _LegoModel:
-    """The reference's GaussianModel getters (scene/gaussian_model.py:179-219) over raw parameters."""
-
-    def __init__(self, raw):
-        self.raw = raw
-        self.active_sh_degree, self.active_sh_degree_t = 3, 2
-        self.time_duration = [0.0, 1.0]
-        self.rot_4d, self.gaussian_dim, self.force_sh_3d, self.prefilter_var = True, 4, False, -1.0
-        self.get_max_sh_channels = 48
-
-    get_xyz = property(lambda s: s.raw["xyz"])
-    get_t = property(lambda s: s.raw["t"])
-    get_scaling = property(lambda s: torch.exp(s.raw["log_s"]))
-    get_scaling_t = property(lambda s: torch.exp(s.raw["log_st"]))
-    get_rotation = property(lambda s: torch.nn.functional.normalize(s.raw["rot"]))
-    get_rotation_r = property(lambda s: torch.nn.functional.normalize(s.raw["rot_r"]))
-    get_opacity = property(lambda s: torch.sigmoid(s.raw["op"]))
-    get_features = property(lambda s: s.raw["sh"])
-
-
-def _lego_render(model, cam, impl):
-    if impl == "ours":
-        from gaussian_renderer import render
-        return render(cam, model, _Pipe(), torch.zeros(3, device=DEV))["render"]
-    import ref_api
-    from fdgs import synth
-    m = model
-    dummy = type("S", (), dict(sh_degree=3, sh_degree_t=2, time_duration=1.0, rot_4d=True, gaussian_dim=4, force_sh_3d=False))
-    st = synth.raster_settings(cam, dummy, device=DEV)
-    means2D = torch.zeros_like(m.get_xyz, requires_grad=True)
-    out = ref_api.rasterize(st, m.get_xyz, means2D, m.get_opacity, m.get_features, torch.zeros(m.get_xyz.shape[0], 2, device=DEV),
-                            m.get_t, m.get_scaling, m.get_scaling_t, m.get_rotation, m.get_rotation_r)
-    return out[0]
+from lego import lego_setup as _lego_setup, LegoModel as _LegoModel, lego_render as _lego_render  # noqa: E402
 
 
 def test_cfg4_training_loop_tracks_reference(C):
