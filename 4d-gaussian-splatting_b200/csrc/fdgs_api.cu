@@ -4,6 +4,7 @@
 // CudaRasterizer::Rasterizer::forward / backward / markVisible
 // (reference: rasterizer_impl.cu:199-364, :368-496, :142-154) and the GeometryState /
 // ImageState / BinningState chunk carving (rasterizer_impl.cu:156-195, rasterizer_impl.h:21-73).
+#include <math.h>
 #include <string.h>
 #include <atomic>
 #include <cstdlib>
@@ -456,6 +457,63 @@ int fdgs_check_rows_zero(int n, const float* const* tensors, const int* widths, 
     FDGS_CUDA(fdgs::launch_rows_zero_check(n, tensors, widths, P, radii, flag, reinterpret_cast<cudaStream_t>(stream_v)),
               "rows_zero_check");
     g_kernel_launches += 1;
+    return FDGS_OK;
+}
+
+int fdgs_l1_ssim_forward(const float* x, const float* y, int C, int H, int W, float* maps, double* sums, void* stream_v) {
+    g_last_error.clear();
+    if (C <= 0 || H <= 0 || W <= 0) return fail(FDGS_ERR_INVALID_ARG, "bad C / H / W");
+    if (!x || !y || !maps || !sums) return fail(FDGS_ERR_INVALID_ARG, "null argument");
+    FDGS_CUDA(fdgs::launch_l1_ssim_fwd(x, y, C, H, W, maps, sums, reinterpret_cast<cudaStream_t>(stream_v)), "l1_ssim_forward");
+    g_kernel_launches += 1;
+    return FDGS_OK;
+}
+
+int fdgs_l1_ssim_backward(const float* x, const float* y, int C, int H, int W, const float* maps, const float* grad_scale,
+                          float lambda_dssim, float* dL_dx, void* stream_v) {
+    g_last_error.clear();
+    if (C <= 0 || H <= 0 || W <= 0) return fail(FDGS_ERR_INVALID_ARG, "bad C / H / W");
+    if (!x || !y || !maps || !dL_dx) return fail(FDGS_ERR_INVALID_ARG, "null argument");
+    FDGS_CUDA(fdgs::launch_l1_ssim_bwd(x, y, C, H, W, maps, grad_scale, lambda_dssim, dL_dx, reinterpret_cast<cudaStream_t>(stream_v)),
+              "l1_ssim_backward");
+    g_kernel_launches += 1;
+    return FDGS_OK;
+}
+
+int fdgs_adam_step(int n, float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                   const int* widths, const float* lrs, long long P, const long long* rows, long long num_rows, long long step,
+                   float beta1, float beta2, float eps, int zero_grad, void* stream_v) {
+    g_last_error.clear();
+    if (n < 0 || n > FDGS_MAX_PACK || P < 0 || step < 1 || (rows && num_rows < 0))
+        return fail(FDGS_ERR_INVALID_ARG, "bad tensor count / row count / step");
+    if (n == 0 || P == 0 || (rows && num_rows == 0)) return FDGS_OK;
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !widths || !lrs) return fail(FDGS_ERR_INVALID_ARG, "null argument");
+    float step_sizes[FDGS_MAX_PACK];
+    // bias corrections in double on the host, like torch.optim.Adam's single-tensor path
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    for (int i = 0; i < n; ++i) {
+        if (!params[i] || !grads[i] || !exp_avg[i] || !exp_avg_sq[i] || widths[i] <= 0)
+            return fail(FDGS_ERR_INVALID_ARG, "bad tensor table entry");
+        step_sizes[i] = (float)((double)lrs[i] / bc1);
+    }
+    FDGS_CUDA(fdgs::launch_adam(n, params, grads, exp_avg, exp_avg_sq, widths, step_sizes, rows ? num_rows : P, rows, beta1, beta2,
+                                eps, (float)sqrt(bc2), zero_grad, reinterpret_cast<cudaStream_t>(stream_v)),
+              "adam_step");
+    g_kernel_launches += 1;
+    return FDGS_OK;
+}
+
+size_t fdgs_knn_scratch_bytes(int n) { return fdgs::knn_scratch_bytes(n > 0 ? n : 0); }
+
+int fdgs_knn(int n, int k, const float* xyz, char* scratch, int* idx, float* dist2, int brute_force, void* stream_v) {
+    g_last_error.clear();
+    if (n < 0 || k < 1 || k > 32) return fail(FDGS_ERR_INVALID_ARG, "bad n / k (1 <= k <= 32)");
+    if (n == 0) return FDGS_OK;
+    if (!xyz || !idx || !dist2 || (!brute_force && !scratch)) return fail(FDGS_ERR_INVALID_ARG, "null argument");
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+    if (brute_force) FDGS_CUDA(fdgs::launch_knn_bruteforce(n, k, xyz, idx, dist2, stream), "knn (brute force)");
+    else FDGS_CUDA(fdgs::launch_knn(n, k, xyz, scratch, idx, dist2, stream), "knn");
+    g_kernel_launches += brute_force ? 1 : 7;
     return FDGS_OK;
 }
 

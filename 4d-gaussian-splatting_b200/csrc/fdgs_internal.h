@@ -196,6 +196,20 @@ cudaError_t launch_rows_zero_check(int n, const float* const* tensors, const int
 cudaError_t launch_pack_rows(bool unpack, int n, float* const* tensors, const int* widths, const long long* block_off,
                              const long long* idx, long long K, float* flat, cudaStream_t stream);
 
+// ---- training-step neighbours of the rasterizer -----------------------------------------
+// fused (1 - lambda) L1 + lambda (1 - SSIM): loss.cu
+cudaError_t launch_l1_ssim_fwd(const float* x, const float* y, int C, int H, int W, float* maps, double* sums, cudaStream_t stream);
+cudaError_t launch_l1_ssim_bwd(const float* x, const float* y, int C, int H, int W, const float* maps, const float* grad_scale,
+                               float lambda_dssim, float* dL_dx, cudaStream_t stream);
+// fused multi-tensor Adam, dense or over listed rows: optim.cu
+cudaError_t launch_adam(int n, float* const* params, float* const* grads, float* const* m, float* const* v, const int* widths,
+                        const float* step_sizes, long long rows, const long long* row_idx, float beta1, float beta2, float eps,
+                        float sqrt_bc2, int zero_grad, cudaStream_t stream);
+// uniform-grid k nearest neighbours: knn.cu
+size_t knn_scratch_bytes(int n);
+cudaError_t launch_knn(int n, int k, const float* xyz, char* scratch, int* idx, float* dist2, cudaStream_t stream);
+cudaError_t launch_knn_bruteforce(int n, int k, const float* xyz, int* idx, float* dist2, cudaStream_t stream);
+
 cudaError_t launch_mark_visible(int P, const float* means3D, const float* viewmatrix, unsigned char* present,
                                 cudaStream_t stream);
 

@@ -405,7 +405,93 @@ void UnpackRows(const torch::Tensor& flat, std::vector<torch::Tensor> tensors, c
           "unpack_rows");
 }
 
+// ---- fused L1 + SSIM (include/fdgs.h: fdgs_l1_ssim_forward / _backward) ------------------------------------------
+// returns (sums double[2] = {sum |x - y|, sum SSIM}, maps float[3,C,H,W])
+std::tuple<torch::Tensor, torch::Tensor> L1SsimForward(const torch::Tensor& x, const torch::Tensor& y) {
+    TORCH_CHECK(x.is_cuda() && y.is_cuda() && x.scalar_type() == torch::kFloat32 && y.scalar_type() == torch::kFloat32,
+                "fdgs: images must be float32 CUDA tensors");
+    TORCH_CHECK(x.dim() == 3 && x.sizes() == y.sizes(), "fdgs: images must be [C,H,W] of equal shape");
+    const c10::cuda::CUDAGuard guard(x.device());
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream().stream();
+    const auto xc = x.contiguous(), yc = y.contiguous();
+    const int C = x.size(0), H = x.size(1), W = x.size(2);
+    torch::Tensor sums = torch::empty({2}, x.options().dtype(torch::kFloat64));
+    torch::Tensor maps = torch::empty({3, C, H, W}, x.options());
+    check(fdgs_l1_ssim_forward(xc.data_ptr<float>(), yc.data_ptr<float>(), C, H, W, maps.data_ptr<float>(),
+                               sums.data_ptr<double>(), (void*)stream),
+          "l1_ssim_forward");
+    return std::make_tuple(sums, maps);
+}
+
+torch::Tensor L1SsimBackward(const torch::Tensor& x, const torch::Tensor& y, const torch::Tensor& maps,
+                             const torch::Tensor& grad_scale, const double lambda_dssim) {
+    const c10::cuda::CUDAGuard guard(x.device());
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream().stream();
+    const auto xc = x.contiguous(), yc = y.contiguous(), gs = grad_scale.to(torch::kFloat32).contiguous();
+    const int C = x.size(0), H = x.size(1), W = x.size(2);
+    torch::Tensor dx = torch::empty({C, H, W}, x.options());
+    check(fdgs_l1_ssim_backward(xc.data_ptr<float>(), yc.data_ptr<float>(), C, H, W, maps.data_ptr<float>(),
+                                gs.numel() ? gs.data_ptr<float>() : nullptr, (float)lambda_dssim, dx.data_ptr<float>(),
+                                (void*)stream),
+          "l1_ssim_backward");
+    return dx;
+}
+
+// ---- fused Adam (include/fdgs.h: fdgs_adam_step) -------------------------------------------------------------------
+void AdamStep(std::vector<torch::Tensor> params, std::vector<torch::Tensor> grads, std::vector<torch::Tensor> exp_avg,
+              std::vector<torch::Tensor> exp_avg_sq, std::vector<double> lrs, const torch::Tensor& rows, const bool sparse,
+              const int64_t step, const double beta1, const double beta2, const double eps, const bool zero_grad) {
+    const size_t n = params.size();
+    TORCH_CHECK(n <= FDGS_MAX_PACK && grads.size() == n && exp_avg.size() == n && exp_avg_sq.size() == n && lrs.size() == n,
+                "fdgs: adam_step table mismatch");
+    if (n == 0) return;
+    const long long P = params[0].size(0);
+    std::vector<float*> p, g, m, v;
+    std::vector<int> widths;
+    std::vector<float> lr;
+    for (size_t i = 0; i < n; ++i) {
+        for (const torch::Tensor* t : {&params[i], &grads[i], &exp_avg[i], &exp_avg_sq[i]})
+            TORCH_CHECK(t->is_cuda() && t->scalar_type() == torch::kFloat32 && t->is_contiguous() && t->size(0) == P &&
+                        t->numel() == params[i].numel(), "fdgs: adam tensors must be contiguous float32 CUDA [P, ...]");
+        p.push_back(params[i].data_ptr<float>()); g.push_back(grads[i].data_ptr<float>());
+        m.push_back(exp_avg[i].data_ptr<float>()); v.push_back(exp_avg_sq[i].data_ptr<float>());
+        widths.push_back(P > 0 ? (int)(params[i].numel() / P) : 1);
+        lr.push_back((float)lrs[i]);
+    }
+    if (sparse) {
+        TORCH_CHECK(rows.is_cuda() && rows.scalar_type() == torch::kInt64 && rows.is_contiguous(), "fdgs: rows must be int64 CUDA");
+        if (rows.numel() == 0) return;
+    }
+    const c10::cuda::CUDAGuard guard(params[0].device());
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream().stream();
+    check(fdgs_adam_step((int)n, p.data(), g.data(), m.data(), v.data(), widths.data(), lr.data(), P,
+                         sparse ? reinterpret_cast<const long long*>(rows.data_ptr<int64_t>()) : nullptr, sparse ? rows.numel() : 0,
+                         step, (float)beta1, (float)beta2, (float)eps, zero_grad, (void*)stream),
+          "adam_step");
+}
+
+// ---- k nearest neighbours (include/fdgs.h: fdgs_knn) ---------------------------------------------------------------
+std::tuple<torch::Tensor, torch::Tensor> Knn(const torch::Tensor& xyz, const int64_t k, const bool brute_force) {
+    TORCH_CHECK(xyz.is_cuda() && xyz.scalar_type() == torch::kFloat32 && xyz.dim() == 2 && xyz.size(1) == 3,
+                "fdgs: xyz must be a float32 CUDA tensor [n,3]");
+    const c10::cuda::CUDAGuard guard(xyz.device());
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream().stream();
+    const auto x = xyz.contiguous();
+    const int n = x.size(0);
+    torch::Tensor idx = torch::empty({n, k}, x.options().dtype(torch::kInt32));
+    torch::Tensor d2 = torch::empty({n, k}, x.options());
+    torch::Tensor scratch = torch::empty({(int64_t)(brute_force ? 16 : fdgs_knn_scratch_bytes(n))}, x.options().dtype(torch::kByte));
+    check(fdgs_knn(n, (int)k, x.data_ptr<float>(), reinterpret_cast<char*>(scratch.data_ptr()), idx.data_ptr<int>(),
+                   d2.data_ptr<float>(), brute_force, (void*)stream),
+          "knn");
+    return std::make_tuple(idx, d2);
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+    m.def("l1_ssim_forward", &L1SsimForward);
+    m.def("l1_ssim_backward", &L1SsimBackward);
+    m.def("adam_step", &AdamStep);
+    m.def("knn", &Knn);
     m.def("pack_rows", &PackRows);
     m.def("unpack_rows", &UnpackRows);
     m.def("rasterize_gaussians", &RasterizeGaussiansCUDA);

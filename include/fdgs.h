@@ -243,6 +243,33 @@ int fdgs_sh_outer_sum(const fdgs_sh_sum_args* args, void* stream);
 int fdgs_check_rows_zero(int n, const float* const* tensors, const int* widths, long long P, const int* radii,
                          int* flag, void* stream);
 
+/* ---- the callers either side of the rasterizer in a training step ---------------------- */
+
+/* Fused photometric loss (reference: utils/loss_utils.py:18-64 l1_loss + ssim, combined as train.py:115-117):
+ *   loss = (1 - lambda) * mean|x - y| + lambda * (1 - mean(SSIM(x, y))),  11x11 Gaussian window, sigma 1.5, zero padding.
+ * forward : sums[0] = sum|x - y|, sums[1] = sum SSIM map (device doubles; loss = combine on the device or host),
+ *           maps[3,C,H,W] = per-pixel partial derivatives kept for the backward.
+ * backward: dL_dx[C,H,W] = grad_scale[0] * d loss / d x   (grad_scale: device scalar, NULL = 1). */
+int fdgs_l1_ssim_forward(const float* x, const float* y, int C, int H, int W, float* maps, double* sums, void* stream);
+int fdgs_l1_ssim_backward(const float* x, const float* y, int C, int H, int W, const float* maps, const float* grad_scale,
+                          float lambda_dssim, float* dL_dx, void* stream);
+
+/* Fused multi-tensor Adam step (reference: torch.optim.Adam(eps=1e-15) over the parameter groups of
+ * scene/gaussian_model.py:331-357, stepped at train.py:248-249).  n <= FDGS_MAX_PACK tensors [P, widths[i]] (device),
+ * one learning rate each; `step` is the 1-based step count (bias correction).  rows = NULL: every row (torch's dense
+ * semantics); otherwise only the `num_rows` listed rows are touched (sparse Adam over the rendered Gaussians).
+ * zero_grad != 0 clears the gradient elements it consumed. */
+int fdgs_adam_step(int n, float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                   const int* widths, const float* lrs, long long P, const long long* rows, long long num_rows,
+                   long long step, float beta1, float beta2, float eps, int zero_grad, void* stream);
+
+/* k nearest neighbours (k <= 32) of every point among the same n points, squared distances ascending, the point
+ * itself first (reference: pointops2 knnquery, pointops2/src/knnquery/knnquery_cuda_kernel.cu:65-107, as called by
+ * utils/general_utils.py:170-184 for the rigidity loss, train.py:132-152).  Uniform-grid search; `scratch` must hold
+ * fdgs_knn_scratch_bytes(n) bytes.  brute_force != 0 runs the reference's O(n^2) scan instead (validation). */
+size_t fdgs_knn_scratch_bytes(int n);
+int fdgs_knn(int n, int k, const float* xyz, char* scratch, int* idx, float* dist2, int brute_force, void* stream);
+
 /* Test/diagnostic hooks (used by tests/ and bench.py only): copy private
  * per-Gaussian / per-instance state out of the scratch buffers into plain
  * caller-provided device arrays so that parity tests can compare them with the

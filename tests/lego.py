@@ -63,18 +63,39 @@ class LegoModel:
 
 
 def lego_render(model, cam, impl):
+    """Both arms run the SAME Python prologue (getters, activations, settings tuple, zero screen-space / flow tensors --
+    the reference's render(), gaussian_renderer/__init__.py:19-194); only the rasterizer underneath differs."""
     if impl == "ours":
         from gaussian_renderer import render
         return render(cam, model, _Pipe(), torch.zeros(3, device=DEV))["render"]
+    return _ref_render(cam, model, torch.zeros(3, device=DEV))["render"]
+
+
+def _ref_render(cam, pc, bg_color):
+    """render() with the compiled reference rasterizer underneath (oracle/ref_api.py); mirrors
+    4d-gaussian-splatting_b200/gaussian_renderer/__init__.py op for op for the all-CUDA branch."""
+    import math
     import ref_api
-    from fdgs import synth
-    m = model
-    dummy = type("S", (), dict(sh_degree=3, sh_degree_t=2, time_duration=1.0, rot_4d=True, gaussian_dim=4, force_sh_3d=False))
-    st = synth.raster_settings(cam, dummy, device=DEV)
-    means2D = torch.zeros_like(m.get_xyz, requires_grad=True)
-    out = ref_api.rasterize(st, m.get_xyz, means2D, m.get_opacity, m.get_features, torch.zeros(m.get_xyz.shape[0], 2, device=DEV),
-                            m.get_t, m.get_scaling, m.get_scaling_t, m.get_rotation, m.get_rotation_r)
-    return out[0]
+    xyz = pc.get_xyz
+    screenspace_points = torch.zeros_like(xyz, dtype=xyz.dtype, requires_grad=True, device=xyz.device) + 0
+    try:
+        screenspace_points.retain_grad()
+    except Exception:
+        pass
+    st = dict(image_height=int(cam.image_height), image_width=int(cam.image_width), tanfovx=math.tan(cam.FoVx * 0.5),
+              tanfovy=math.tan(cam.FoVy * 0.5), bg=bg_color, scale_modifier=1.0, viewmatrix=cam.world_view_transform,
+              projmatrix=cam.full_proj_transform, sh_degree=pc.active_sh_degree, sh_degree_t=pc.active_sh_degree_t,
+              campos=cam.camera_center, timestamp=cam.timestamp, time_duration=pc.time_duration[1] - pc.time_duration[0],
+              rot_4d=pc.rot_4d, gaussian_dim=pc.gaussian_dim, force_sh_3d=pc.force_sh_3d, prefiltered=False, debug=False)
+    opacity = pc.get_opacity
+    scales, rotations = pc.get_scaling, pc.get_rotation
+    scales_t, ts, rotations_r = pc.get_scaling_t, pc.get_t, pc.get_rotation_r
+    shs = pc.get_features
+    flow_2d = torch.zeros_like(xyz[:, :2])
+    color, radii, depth, alpha, flow, _ = ref_api.rasterize(st, xyz, screenspace_points, opacity, shs, flow_2d, ts, scales,
+                                                            scales_t, rotations, rotations_r)
+    return {"render": color, "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "radii": radii,
+            "depth": depth, "alpha": alpha, "flow": flow}
 
 
 def make_optimizer(raw):

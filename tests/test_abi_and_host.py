@@ -14,7 +14,7 @@ import helpers
 def _header_symbols(root):
     text = open(os.path.join(root, "include", "fdgs.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(fdgs_[a-z_]+)\s*\(", text)) - {"fdgs_alloc_fn"})
+    return sorted(set(re.findall(r"\b(fdgs_[a-z_0-9]+)\s*\(", text)) - {"fdgs_alloc_fn"})
 
 
 def test_header_declares_expected_entry_points(repo_root):
