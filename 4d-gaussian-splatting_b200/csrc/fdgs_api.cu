@@ -43,6 +43,8 @@ constexpr size_t kMaxProfEvents = 4096;
 std::atomic<long long> g_kernel_launches{0};
 // FDGS_TRACE=1 + debug=true: print every stage to stderr before and after its synchronisation
 const bool g_trace = getenv("FDGS_TRACE") != nullptr;
+// summation order of the quaternion norm in the raw-parameter entry (fdgs_common.cuh: quat_norm); 0 = ATen's order
+const int g_quat_norm_mode = getenv("FDGS_NORMALIZE_MODE") ? atoi(getenv("FDGS_NORMALIZE_MODE")) : 0;
 
 struct StageTimer {
     cudaEvent_t a = nullptr, b = nullptr;
@@ -276,6 +278,10 @@ int fdgs_forward(const fdgs_forward_args* a, fdgs_alloc_fn geom_alloc, void* geo
         pp.focal_x = W / (2.0f * a->tan_fovx);
         pp.grid_x = grid_x; pp.grid_y = grid_y; pp.prefiltered = a->prefiltered;
         sh_staging(a->colors_precomp ? nullptr : a->shs, a->M, true, &pp.sh_bulk_ok, &pp.sh_row_stride_floats);
+        pp.raw_params = a->raw_params; pp.quat_norm_mode = g_quat_norm_mode;
+        pp.shs_rest = a->colors_precomp ? nullptr : a->shs_rest;
+        if (pp.shs_rest && a->M < 2) return fail(FDGS_ERR_INVALID_ARG, "split SH rows need M >= 2");
+        if (a->raw_params && a->cov3D_precomp) return fail(FDGS_ERR_INVALID_ARG, "raw_params needs scales / rotations, not cov3D_precomp");
         pp.flows = a->flows_precomp;
         pp.out_means3D = a->out_means3D; pp.radii = a->radii; pp.cov3D = geom.cov3D; pp.grec = geom.grec;
         pp.clamped = geom.clamped; pp.tiles_touched = geom.tiles_touched; pp.binrec = geom.binrec;
@@ -377,6 +383,10 @@ int fdgs_backward(const fdgs_backward_args* a, void* stream_v) {
     pb.grec = geom.grec; pb.blend_raw = blend_raw ? 1 : 0; pb.W = W; pb.H = H;
     sh_staging(a->shs, a->M, false, &pb.sh_bulk_ok, &pb.sh_row_stride_floats);
     if (a->dL_dsh && (reinterpret_cast<uintptr_t>(a->dL_dsh) % 16) != 0) pb.sh_bulk_ok = 0;
+    pb.raw_params = a->raw_params; pb.quat_norm_mode = g_quat_norm_mode;
+    pb.shs_rest = a->shs ? a->shs_rest : nullptr; pb.dL_dsh_rest = a->dL_dsh_rest;
+    if (pb.shs_rest && a->dL_dsh && !a->dL_dsh_rest) return fail(FDGS_ERR_INVALID_ARG, "split SH rows need dL_dsh_rest");
+    if (!pb.shs_rest && a->dL_dsh_rest) return fail(FDGS_ERR_INVALID_ARG, "dL_dsh_rest without shs_rest");
     pb.dL_dmean2D = a->dL_dmean2D; pb.dL_dconic = a->dL_dconic; pb.dL_dopacity = a->dL_dopacity; pb.dL_dcolor = a->dL_dcolor;
     pb.dL_dmean3D = a->dL_dmean3D; pb.dL_dcov3D = a->dL_dcov3D; pb.dL_dsh = a->dL_dsh; pb.sh_factors = a->sh_factors;
     pb.dL_dts = a->dL_dts;

@@ -52,6 +52,38 @@ struct Camera {
     float cam[3];
 };
 
+// ---- parameter activations (raw-parameter entry) ---------------------------------
+// The reference applies these in PyTorch before every render (scene/gaussian_model.py:179-219 getters:
+// scaling_activation = torch.exp, opacity_activation = torch.sigmoid, rotation_activation = F.normalize); with
+// fdgs_forward_args.raw_params the kernels apply them to the raw parameters instead.  Spelled like the ATen CUDA
+// kernels so that the activated values -- and with them radii, tiles, depth order -- do not change:
+//   exp      : expf (full-precision libdevice, what std::exp resolves to in ATen's exp kernel)
+//   sigmoid  : 1 / (1 + expf(-x))                                  (ATen sigmoid kernel, opmath = float)
+//   normalize: q / max(||q||_2, 1e-12); ATen reduces the 4 squares of a row with 4 cooperating lanes and a
+//              shuffle tree, i.e. (x^2 + y^2) + (z^2 + w^2)          (norm_kernel + block_x_reduce, dim 4)
+__device__ __forceinline__ float act_exp(float x) { return expf(x); }
+__device__ __forceinline__ float act_sigmoid(float x) { return fdiv(1.0f, fadd(1.0f, expf(-x))); }
+__device__ __forceinline__ float quat_norm(const float4 q, int mode) {
+    float s;
+    if (mode == 1) s = fadd(fadd(fadd(fmul(q.x, q.x), fmul(q.y, q.y)), fmul(q.z, q.z)), fmul(q.w, q.w));   // sequential
+    else if (mode == 2) s = ffma(q.w, q.w, ffma(q.z, q.z, ffma(q.y, q.y, fmul(q.x, q.x))));                 // fma chain
+    else s = fadd(fadd(fmul(q.x, q.x), fmul(q.y, q.y)), fadd(fmul(q.z, q.z), fmul(q.w, q.w)));              // pairwise tree
+    return fsqrt(s);
+}
+__device__ __forceinline__ float4 act_normalize(const float4 q, int mode) {
+    const float d = fmaxf(quat_norm(q, mode), 1e-12f);
+    return make_float4(fdiv(q.x, d), fdiv(q.y, d), fdiv(q.z, d), fdiv(q.w, d));
+}
+// gradient w.r.t. the raw quaternion given the gradient g w.r.t. the normalised one (autograd of q / clamp_min(||q||, eps))
+__device__ __forceinline__ float4 act_normalize_bwd(const float4 q, const float4 g, int mode) {
+    const float n = quat_norm(q, mode);
+    const float d = fmaxf(n, 1e-12f);
+    const float inv = 1.0f / d;
+    const float dot = g.x * q.x + g.y * q.y + g.z * q.z + g.w * q.w;
+    const float coef = (n > 1e-12f) ? -dot * inv * inv / n : 0.f;
+    return make_float4(g.x * inv + coef * q.x, g.y * inv + coef * q.y, g.z * inv + coef * q.z, g.w * inv + coef * q.w);
+}
+
 // ---- 4D covariance slice -----------------------------------------------------------------
 // reference: forward.cu:279-352 computeCov3D_conditional.  Produces the 10 distinct entries of
 // Sigma = (S R)^T (S R), R = M_r * M_l, in the reference's evaluation order.

@@ -55,6 +55,9 @@ struct PreprocessFwdParams {
     int prefiltered;
     int sh_bulk_ok;             // SH rows can be streamed with cp.async.bulk (16-byte aligned rows)
     int sh_row_stride_floats;   // padded shared-memory row stride (multiple of 4 floats)
+    int raw_params;             // scales / scales_t are log-scales, rotations un-normalised, opacities logits
+    int quat_norm_mode;         // summation order of the quaternion norm (fdgs_common.cuh: quat_norm)
+    const float* shs_rest;      // non-NULL: SH row split as shs = [P,1,3] (dc) | shs_rest = [P,M-1,3]
     // outputs
     const float* flows;     // [P,2] or NULL
     float* out_means3D;
@@ -148,6 +151,10 @@ struct PreprocessBwdParams {
     int has_scales;         // scales != NULL in the reference's sense (backward.cu:908)
     int sh_bulk_ok;         // SH rows are 16-byte aligned and 16-byte multiples: stream with cp.async.bulk
     int sh_row_stride_floats;
+    int raw_params;         // as in the forward: gradients then come out w.r.t. the RAW parameters
+    int quat_norm_mode;
+    const float* shs_rest;  // split SH input (see PreprocessFwdParams)
+    float* dL_dsh_rest;     // [P,M-1,3] when shs_rest is given (dL_dsh is then [P,1,3])
     float* dL_dmean2D;      // in/out when blend_raw
     float* dL_dconic;       // in/out when blend_raw
     float* dL_dopacity;     // in/out

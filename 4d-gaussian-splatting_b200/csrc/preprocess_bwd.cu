@@ -207,8 +207,13 @@ __device__ __forceinline__ void sh_row_inplace(float4* rowq, int nq, const ShCtx
 // only the 3-float colour factor is written (sh_factors[P,3], zeros for Gaussians this view did not render); the rows
 // of all views are rebuilt and summed after the exchange by sh_outer_sum_kernel (exchange.cu).  The SH row is still
 // read: the direction / time gradients need sum_k dbasis_k (sh_k . dRGB).
-template <bool BULK, bool FACTORS>
+// STAGE as in preprocess_fwd_kernel: 0 = global memory coefficient by coefficient, 1 = cp.async.bulk rows in and out,
+// 2 = cooperative coalesced copies of split rows (features_dc | features_rest in, their two gradient tensors out).
+template <int STAGE, bool FACTORS>
 __global__ void __launch_bounds__(SB_THREADS, 6) sh_bwd_kernel(const PreprocessBwdParams a) {
+    constexpr bool BULK = STAGE == 1;
+    constexpr bool SPLIT = STAGE == 2;
+    __shared__ int slot_idx[SB_CAP];   // STAGE 2: Gaussian whose row occupies each slot
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ short slot_of[SB_THREADS];   // rank among the rendered rows of this CTA, -1 = not rendered
@@ -246,6 +251,18 @@ __global__ void __launch_bounds__(SB_THREADS, 6) sh_bwd_kernel(const PreprocessB
             a.sh_factors[3 * idx + 1] = 0.f;
             a.sh_factors[3 * idx + 2] = 0.f;
         }
+    } else if (a.dL_dsh_rest != nullptr) {
+        // split gradient tensors: [P,1,3] and [P,M-1,3]
+        const int rows_here = min(SB_THREADS, a.P - blockIdx.x * SB_THREADS);
+        const size_t r0 = (size_t)blockIdx.x * SB_THREADS;
+        const int rest_floats = row_floats - 3;
+        for (int f = tid; f < rows_here * row_floats; f += SB_THREADS) {
+            const int r = f / row_floats, c = f - r * row_floats;
+            if (slot_of[r] < 0) {
+                if (c < 3) a.dL_dsh[(r0 + r) * 3 + c] = 0.f;
+                else a.dL_dsh_rest[(r0 + r) * rest_floats + (c - 3)] = 0.f;
+            }
+        }
     } else {
         const int rows_here = min(SB_THREADS, a.P - blockIdx.x * SB_THREADS);
         float4* dst = reinterpret_cast<float4*>(a.dL_dsh + (size_t)blockIdx.x * SB_THREADS * row_floats);
@@ -274,24 +291,37 @@ __global__ void __launch_bounds__(SB_THREADS, 6) sh_bwd_kernel(const PreprocessB
         }
     }
 
-    if (BULK) {
+    if (STAGE != 0) {
         float* rows = reinterpret_cast<float*>(smem_raw);
+        const int rest_floats = row_floats - 3;
         for (int round = 0, lo = 0; lo < nvis; ++round, lo += SB_CAP) {
             const int cnt = min(SB_CAP, nvis - lo);
             const bool mine = vis && my_rank >= lo && my_rank < lo + cnt;
             float4* rowq = reinterpret_cast<float4*>(rows + (size_t)(my_rank - lo) * a.sh_row_stride_floats);
             if (round > 0) {
                 // the previous round's bulk stores must have finished reading the slots
-                if (!FACTORS && vis) bulk_wait_read_all();
+                if (BULK && !FACTORS && vis) bulk_wait_read_all();
                 __syncthreads();
             }
-            if (tid == 0) mbar_expect_tx(&bar, (uint32_t)cnt * (uint32_t)row_floats * 4u);
-            if (mine) bulk_g2s(rowq, a.shs + (size_t)idx * row_floats, (uint32_t)row_floats * 4u, &bar);
+            if (BULK) {
+                if (tid == 0) mbar_expect_tx(&bar, (uint32_t)cnt * (uint32_t)row_floats * 4u);
+                if (mine) bulk_g2s(rowq, a.shs + (size_t)idx * row_floats, (uint32_t)row_floats * 4u, &bar);
+            } else {
+                if (mine) slot_idx[my_rank - lo] = idx;
+                __syncthreads();
+                for (int sidx = 0; sidx < cnt; ++sidx) {
+                    const size_t g = (size_t)slot_idx[sidx];
+                    float* dst = rows + (size_t)sidx * a.sh_row_stride_floats;
+                    for (int f = tid; f < row_floats; f += SB_THREADS)
+                        dst[f] = (f < 3) ? __ldg(a.shs + g * 3 + f) : __ldg(a.shs_rest + g * rest_floats + (f - 3));
+                }
+                __syncthreads();
+            }
             if (mine) {
-                mbar_wait(&bar, (uint32_t)round & 1u);
+                if (BULK) mbar_wait(&bar, (uint32_t)round & 1u);
                 float ddx, ddy, ddz, dtt;
                 sh_row_inplace<!FACTORS>(rowq, nq, c, ddx, ddy, ddz, dtt);
-                if (!FACTORS) {
+                if (BULK && !FACTORS) {
                     fence_async_smem();
                     bulk_s2g(a.dL_dsh + (size_t)idx * row_floats, rowq, (uint32_t)row_floats * 4u);
                     bulk_commit();
@@ -302,12 +332,28 @@ __global__ void __launch_bounds__(SB_THREADS, 6) sh_bwd_kernel(const PreprocessB
                 a.dL_dmean3D[3 * idx + 2] = dm.z;
                 a.dL_dts[idx] = c.sh4d ? dtt : 0.f;
             }
+            if (SPLIT && !FACTORS) {
+                // the gradient rows, now in the slots, go out the way the rows came in: coalesced, split over the two tensors
+                __syncthreads();
+                for (int sidx = 0; sidx < cnt; ++sidx) {
+                    const size_t g = (size_t)slot_idx[sidx];
+                    const float* src = rows + (size_t)sidx * a.sh_row_stride_floats;
+                    for (int f = tid; f < row_floats; f += SB_THREADS) {
+                        if (f < 3) a.dL_dsh[g * 3 + f] = src[f];
+                        else a.dL_dsh_rest[g * rest_floats + (f - 3)] = src[f];
+                    }
+                }
+            }
         }
-        if (!FACTORS && vis) bulk_wait_all();
+        if (BULK && !FACTORS && vis) bulk_wait_all();
     } else if (vis) {
         // generic path: global loads / stores, one coefficient at a time
-        const float* grow = a.shs + (size_t)idx * row_floats;
-        float* drow = FACTORS ? nullptr : a.dL_dsh + (size_t)idx * row_floats;
+        // generic path; with split rows coefficient 0 lives in shs / dL_dsh [P,1,3], the others in *_rest [P,M-1,3]
+        const bool split = a.shs_rest != nullptr;
+        const float* grow = split ? a.shs_rest + (size_t)idx * (row_floats - 3) - 3 : a.shs + (size_t)idx * row_floats;
+        const float* grow0 = split ? a.shs + (size_t)idx * 3 : grow;
+        float* drow = FACTORS ? nullptr : (split ? a.dL_dsh_rest + (size_t)idx * (row_floats - 3) - 3 : a.dL_dsh + (size_t)idx * row_floats);
+        float* drow0 = FACTORS ? nullptr : (split ? a.dL_dsh + (size_t)idx * 3 : drow);
         float ddx = 0.f, ddy = 0.f, ddz = 0.f, dtt = 0.f;
         ShDeriv SDg;
         sh_basis_deriv(c.dirn.x, c.dirn.y, c.dirn.z, c.deg, SDg);
@@ -318,15 +364,16 @@ __global__ void __launch_bounds__(SB_THREADS, 6) sh_bwd_kernel(const PreprocessB
                 const int cidx = blk * 16 + k;
                 float w = 0.f;
                 if (blk_on && k < c.ncoef) {
-                    const float sk = __ldg(grow + 3 * cidx) * c.dRGB[0] + __ldg(grow + 3 * cidx + 1) * c.dRGB[1] +
-                                     __ldg(grow + 3 * cidx + 2) * c.dRGB[2];
+                    const float* gsrc = (cidx == 0) ? grow0 : grow + 3 * cidx;
+                    const float sk = __ldg(gsrc) * c.dRGB[0] + __ldg(gsrc + 1) * c.dRGB[1] + __ldg(gsrc + 2) * c.dRGB[2];
                     sx += SDg.dx[k] * sk; sy += SDg.dy[k] * sk; sz += SDg.dz[k] * sk; sl += SDg.l[k] * sk;
                     w = (blk == 0) ? ((c.sh4d && k == 1) ? SDg.l[0] : SDg.l[k]) : c.tw[blk < 3 ? blk : 0] * SDg.l[k];
                 }
                 if (!FACTORS) {
-                    drow[3 * cidx + 0] = w * c.dRGB[0];
-                    drow[3 * cidx + 1] = w * c.dRGB[1];
-                    drow[3 * cidx + 2] = w * c.dRGB[2];
+                    float* dd = (cidx == 0) ? drow0 : drow + 3 * cidx;
+                    dd[0] = w * c.dRGB[0];
+                    dd[1] = w * c.dRGB[1];
+                    dd[2] = w * c.dRGB[2];
                 }
             }
             if (blk_on) {
@@ -598,14 +645,20 @@ __global__ void __launch_bounds__(GB_THREADS, 8) geom_bwd_kernel(const Preproces
         // ---------------- covariance backward ----------------
         if (a.has_scales) {
             const float mod = a.scale_modifier;
+            const bool raw = a.raw_params != 0;
+            auto scale_in = [&](const float* sp, int i) { const float v = sp[i]; return raw ? act_exp(v) : v; };
+            auto quat_in = [&](const float* qp) {
+                const float4 q = reinterpret_cast<const float4*>(qp)[idx];
+                return raw ? act_normalize(q, a.quat_norm_mode) : q;
+            };
             if (a.rot_4d) {
                 // backward.cu:689-834
                 const float t = a.ts[idx];
                 const float dt = fsub(a.timestamp, t);
-                const float4 rot = reinterpret_cast<const float4*>(a.rotations)[idx];
-                const float4 rotr = reinterpret_cast<const float4*>(a.rotations_r)[idx];
-                const float sc[4] = {fmul(mod, a.scales[3 * idx + 0]), fmul(mod, a.scales[3 * idx + 1]),
-                                     fmul(mod, a.scales[3 * idx + 2]), fmul(mod, a.scales_t[idx])};
+                const float4 rot = quat_in(a.rotations);
+                const float4 rotr = quat_in(a.rotations_r);
+                const float sc[4] = {fmul(mod, scale_in(a.scales, 3 * idx + 0)), fmul(mod, scale_in(a.scales, 3 * idx + 1)),
+                                     fmul(mod, scale_in(a.scales, 3 * idx + 2)), fmul(mod, scale_in(a.scales_t, idx))};
                 Sigma4 S;
                 float R4[4][4];
                 build_M4<true>(sc[0], sc[1], sc[2], sc[3], rot, rotr, S.M, R4);
@@ -625,7 +678,7 @@ __global__ void __launch_bounds__(GB_THREADS, 8) geom_bwd_kernel(const Preproces
                                   (cov_t * cov_t);
                     // opacity -> marginal chain (:769-774)
                     const float dop = a.dL_dopacity[idx];
-                    const float dmarg = dop * a.opacities[idx];
+                    const float dmarg = dop * (raw ? act_sigmoid(a.opacities[idx]) : a.opacities[idx]);
                     a.dL_dopacity[idx] = dop * marginal;
                     const float dmarg_dcovt = marginal * dt * dt / 2 / (ctp * ctp);
                     const float dmarg_dt = marginal * dt / ctp;
@@ -686,8 +739,9 @@ __global__ void __launch_bounds__(GB_THREADS, 8) geom_bwd_kernel(const Preproces
                 }
             } else {
                 // backward.cu:621-684 (and no marginal-opacity gradient for non-rot 4D, :917-919)
-                const float4 q = reinterpret_cast<const float4*>(a.rotations)[idx];
-                const float sc[3] = {mod * a.scales[3 * idx + 0], mod * a.scales[3 * idx + 1], mod * a.scales[3 * idx + 2]};
+                const float4 q = quat_in(a.rotations);
+                const float sc[3] = {mod * scale_in(a.scales, 3 * idx + 0), mod * scale_in(a.scales, 3 * idx + 1),
+                                     mod * scale_in(a.scales, 3 * idx + 2)};
                 const float r = q.x, x = q.y, y = q.z, z = q.w;
                 float R[3][3] = {{1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
                                  {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
@@ -721,6 +775,26 @@ __global__ void __launch_bounds__(GB_THREADS, 8) geom_bwd_kernel(const Preproces
                 g_rot[3] = 2 * r * (Nt[0][1] - Nt[1][0]) + 2 * x * (Nt[2][0] + Nt[0][2]) + 2 * y * (Nt[1][2] + Nt[2][1]) -
                            4 * z * (Nt[1][1] + Nt[0][0]);
             }
+            if (raw) {
+                // chain through the activations the forward applied (autograd of exp / F.normalize in the reference's
+                // getters, scene/gaussian_model.py:179-219): gradients now refer to the RAW parameters
+#pragma unroll
+                for (int i = 0; i < 3; ++i) g_scale[i] *= act_exp(a.scales[3 * idx + i]);
+                if (a.scales_t) g_scale_t *= act_exp(a.scales_t[idx]);
+                const float4 gq = act_normalize_bwd(reinterpret_cast<const float4*>(a.rotations)[idx],
+                                                    make_float4(g_rot[0], g_rot[1], g_rot[2], g_rot[3]), a.quat_norm_mode);
+                g_rot[0] = gq.x; g_rot[1] = gq.y; g_rot[2] = gq.z; g_rot[3] = gq.w;
+                if (a.rot_4d) {
+                    const float4 gr = act_normalize_bwd(reinterpret_cast<const float4*>(a.rotations_r)[idx],
+                                                        make_float4(g_rotr[0], g_rotr[1], g_rotr[2], g_rotr[3]), a.quat_norm_mode);
+                    g_rotr[0] = gr.x; g_rotr[1] = gr.y; g_rotr[2] = gr.z; g_rotr[3] = gr.w;
+                }
+            }
+        }
+        if (a.raw_params) {
+            // d sigmoid: dL/dlogit = dL/dopacity * (1 - o) * o   (torch's sigmoid_backward)
+            const float o = act_sigmoid(a.opacities[idx]);
+            a.dL_dopacity[idx] = a.dL_dopacity[idx] * (1.f - o) * o;
         }
     }
 
@@ -758,17 +832,26 @@ cudaError_t launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t str
     const bool has_sh = p.shs != nullptr && p.M > 0 && (p.dL_dsh != nullptr || factors);
     if (has_sh) {
         const int blocks = (p.P + SB_THREADS - 1) / SB_THREADS;
-        if (p.sh_bulk_ok) {
+        const bool split = p.shs_rest != nullptr;
+        if (p.sh_bulk_ok && (!split || p.M % 16 == 0)) {
             const size_t smem = (size_t)SB_CAP * p.sh_row_stride_floats * sizeof(float);
-            static PerDeviceOnce once, once_f;
-            cudaError_t e0 = factors ? ensure_dynamic_smem(sh_bwd_kernel<true, true>, 200 * 1024, once_f)
-                                     : ensure_dynamic_smem(sh_bwd_kernel<true, false>, 200 * 1024, once);
+            static PerDeviceOnce once[4];
+            cudaError_t e0;
+            if (split) e0 = factors ? ensure_dynamic_smem(sh_bwd_kernel<2, true>, 200 * 1024, once[3])
+                                    : ensure_dynamic_smem(sh_bwd_kernel<2, false>, 200 * 1024, once[2]);
+            else e0 = factors ? ensure_dynamic_smem(sh_bwd_kernel<1, true>, 200 * 1024, once[1])
+                              : ensure_dynamic_smem(sh_bwd_kernel<1, false>, 200 * 1024, once[0]);
             if (e0 != cudaSuccess) return e0;
-            if (factors) sh_bwd_kernel<true, true><<<blocks, SB_THREADS, smem, stream>>>(p);
-            else sh_bwd_kernel<true, false><<<blocks, SB_THREADS, smem, stream>>>(p);
+            if (split) {
+                if (factors) sh_bwd_kernel<2, true><<<blocks, SB_THREADS, smem, stream>>>(p);
+                else sh_bwd_kernel<2, false><<<blocks, SB_THREADS, smem, stream>>>(p);
+            } else {
+                if (factors) sh_bwd_kernel<1, true><<<blocks, SB_THREADS, smem, stream>>>(p);
+                else sh_bwd_kernel<1, false><<<blocks, SB_THREADS, smem, stream>>>(p);
+            }
         } else {
-            if (factors) sh_bwd_kernel<false, true><<<blocks, SB_THREADS, 0, stream>>>(p);
-            else sh_bwd_kernel<false, false><<<blocks, SB_THREADS, 0, stream>>>(p);
+            if (factors) sh_bwd_kernel<0, true><<<blocks, SB_THREADS, 0, stream>>>(p);
+            else sh_bwd_kernel<0, false><<<blocks, SB_THREADS, 0, stream>>>(p);
         }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;

@@ -75,12 +75,14 @@ struct RowSmem {
     }
 };
 struct RowGmem {
-    const float* p;   // global row (any alignment, any M)
+    const float* p;    // global row (any alignment, any M); with a split row: its first 3 floats (features_dc)
+    const float* p1;   // NULL, or the remaining 3 (M - 1) floats of a split row (features_rest)
     __device__ __forceinline__ void load_block(int blk, int M, float v[48]) const {
 #pragma unroll
         for (int i = 0; i < 48; ++i) {
             const int k = blk * 48 + i;
-            v[i] = (k < 3 * M) ? __ldg(p + k) : 0.f;
+            if (p1 == nullptr) v[i] = (k < 3 * M) ? __ldg(p + k) : 0.f;
+            else v[i] = (k < 3) ? __ldg(p + k) : ((k < 3 * M) ? __ldg(p1 + (k - 3)) : 0.f);
         }
     }
 };
@@ -174,11 +176,17 @@ __device__ __forceinline__ void sh_color_3d(const Row& row, int M, int deg, floa
     }
 }
 
-template <bool BULK>
+// STAGE: how the SH rows of the rendered Gaussians reach shared memory -- 0: not at all (read from global memory
+// coefficient by coefficient: odd row sizes), 1: one cp.async.bulk per row (TMA 1-D; contiguous 16-byte-aligned rows),
+// 2: cooperative coalesced copy by the whole CTA (split rows features_dc | features_rest of the raw-parameter entry:
+// 12-byte and 564-byte pieces, which the bulk-copy engine cannot address).
+template <int STAGE>
 __global__ void __launch_bounds__(PRE_THREADS, 5) preprocess_fwd_kernel(const PreprocessFwdParams a) {
+    constexpr bool BULK = STAGE == 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ int warp_cnt[PRE_THREADS / 32];
+    __shared__ int slot_idx[PRE_CAP];   // STAGE 2: Gaussian whose row occupies each slot
 
     const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
     const bool in_range = idx < a.P;
@@ -204,6 +212,14 @@ __global__ void __launch_bounds__(PRE_THREADS, 5) preprocess_fwd_kernel(const Pr
         oy = my = a.means3D[3 * idx + 1];
         oz = mz = a.means3D[3 * idx + 2];
         opacity = a.opacities[idx];
+        const bool raw = a.raw_params != 0;
+        if (raw) opacity = act_sigmoid(opacity);
+        // scales / rotations as the covariance code below sees them: activated here when the caller passed raw parameters
+        auto scale_in = [&](const float* sp, int i) { const float v = sp[i]; return raw ? act_exp(v) : v; };
+        auto quat_in = [&](const float* qp) {
+            const float4 q = reinterpret_cast<const float4*>(qp)[idx];
+            return raw ? act_normalize(q, a.quat_norm_mode) : q;
+        };
         bool alive = true;
         float c3[6];
         if (a.cov3D_precomp != nullptr) {
@@ -212,11 +228,11 @@ __global__ void __launch_bounds__(PRE_THREADS, 5) preprocess_fwd_kernel(const Pr
         } else if (a.rot_4d) {
             // forward.cu:279-352
             const float dt = fsub(a.timestamp, a.ts[idx]);
-            const float4 rot = reinterpret_cast<const float4*>(a.rotations)[idx];
-            const float4 rotr = reinterpret_cast<const float4*>(a.rotations_r)[idx];
+            const float4 rot = quat_in(a.rotations);
+            const float4 rotr = quat_in(a.rotations_r);
             Sigma4 S;
-            build_M4(fmul(a.scale_modifier, a.scales[3 * idx + 0]), fmul(a.scale_modifier, a.scales[3 * idx + 1]),
-                     fmul(a.scale_modifier, a.scales[3 * idx + 2]), fmul(a.scale_modifier, a.scales_t[idx]), rot,
+            build_M4(fmul(a.scale_modifier, scale_in(a.scales, 3 * idx + 0)), fmul(a.scale_modifier, scale_in(a.scales, 3 * idx + 1)),
+                     fmul(a.scale_modifier, scale_in(a.scales, 3 * idx + 2)), fmul(a.scale_modifier, scale_in(a.scales_t, idx)), rot,
                      rotr, S.M);
             sigma_from_M(S);
             const float cov_t = S.s33;
@@ -240,15 +256,14 @@ __global__ void __launch_bounds__(PRE_THREADS, 5) preprocess_fwd_kernel(const Pr
         } else {
             // forward.cu:242-276 and :431-437
             float M3[3][3];
-            build_M3(fmul(a.scale_modifier, a.scales[3 * idx + 0]), fmul(a.scale_modifier, a.scales[3 * idx + 1]),
-                     fmul(a.scale_modifier, a.scales[3 * idx + 2]), reinterpret_cast<const float4*>(a.rotations)[idx],
-                     M3);
+            build_M3(fmul(a.scale_modifier, scale_in(a.scales, 3 * idx + 0)), fmul(a.scale_modifier, scale_in(a.scales, 3 * idx + 1)),
+                     fmul(a.scale_modifier, scale_in(a.scales, 3 * idx + 2)), quat_in(a.rotations), M3);
             cov3_from_M3(M3, c3);
 #pragma unroll
             for (int i = 0; i < 6; ++i) a.cov3D[6 * idx + i] = c3[i];
             if (a.gaussian_dim == 4) {
                 const float dt = fsub(a.ts[idx], a.timestamp);
-                const float sigma = fmul(a.scale_modifier, a.scales_t[idx]);
+                const float sigma = fmul(a.scale_modifier, scale_in(a.scales_t, idx));
                 const float marginal = marginal_from(dt, sigma, a.prefilter_var);
                 if ((double)marginal <= 0.05) alive = false;
                 else opacity = fmul(opacity, marginal);
@@ -329,7 +344,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 5) preprocess_fwd_kernel(const Pr
                 else rgb[ch] = r;
             }
         };
-        if (BULK) {
+        if (STAGE != 0) {
             // Only the rows of RENDERED Gaussians are fetched, into PRE_CAP shared-memory slots handed out by a
             // block-level compaction (typically a third of a CTA's Gaussians are rendered): a third of the
             // shared memory of a slot-per-thread layout, so twice the CTAs per SM stay resident to hide the
@@ -351,16 +366,31 @@ __global__ void __launch_bounds__(PRE_THREADS, 5) preprocess_fwd_kernel(const Pr
                 const int cnt = min(PRE_CAP, nvis - lo);
                 const bool mine = visible && my_rank >= lo && my_rank < lo + cnt;
                 if (round > 0) __syncthreads();   // the previous round's readers are done with the slots
-                if (threadIdx.x == 0) mbar_expect_tx(&bar, (uint32_t)cnt * (uint32_t)row_floats * 4u);
-                if (mine) {
-                    float* slot = rows + (size_t)(my_rank - lo) * stride;
-                    bulk_g2s(slot, a.shs + (size_t)idx * row_floats, (uint32_t)row_floats * 4u, &bar);
-                    mbar_wait(&bar, (uint32_t)round & 1u);
-                    eval(RowSmem{reinterpret_cast<const float4*>(slot)});
+                float* slot = rows + (size_t)(my_rank - lo) * stride;
+                if (BULK) {
+                    if (threadIdx.x == 0) mbar_expect_tx(&bar, (uint32_t)cnt * (uint32_t)row_floats * 4u);
+                    if (mine) {
+                        bulk_g2s(slot, a.shs + (size_t)idx * row_floats, (uint32_t)row_floats * 4u, &bar);
+                        mbar_wait(&bar, (uint32_t)round & 1u);
+                    }
+                } else {
+                    // split rows: every thread of the CTA copies, row by row, coalesced 4-byte words
+                    if (mine) slot_idx[my_rank - lo] = idx;
+                    __syncthreads();
+                    const int rest_floats = row_floats - 3;
+                    for (int sidx = 0; sidx < cnt; ++sidx) {
+                        const size_t g = (size_t)slot_idx[sidx];
+                        float* dst = rows + (size_t)sidx * stride;
+                        for (int f = threadIdx.x; f < row_floats; f += PRE_THREADS)
+                            dst[f] = (f < 3) ? __ldg(a.shs + g * 3 + f) : __ldg(a.shs_rest + g * rest_floats + (f - 3));
+                    }
+                    __syncthreads();
                 }
+                if (mine) eval(RowSmem{reinterpret_cast<const float4*>(slot)});
             }
         } else if (visible) {
-            eval(RowGmem{a.shs + (size_t)idx * row_floats});
+            if (a.shs_rest) eval(RowGmem{a.shs + (size_t)idx * 3, a.shs_rest + (size_t)idx * (row_floats - 3)});
+            else eval(RowGmem{a.shs + (size_t)idx * row_floats, nullptr});
         }
     } else if (visible) {
         rgb[0] = a.colors_precomp[3 * idx + 0];
@@ -411,15 +441,21 @@ __global__ void __launch_bounds__(PRE_THREADS, 5) preprocess_fwd_kernel(const Pr
 cudaError_t launch_preprocess_fwd(const PreprocessFwdParams& p, cudaStream_t stream) {
     if (p.P <= 0) return cudaSuccess;
     const int blocks = (p.P + PRE_THREADS - 1) / PRE_THREADS;
-    const bool bulk = p.sh_bulk_ok && p.colors_precomp == nullptr;
-    if (bulk) {
+    const bool staged = p.sh_bulk_ok && p.colors_precomp == nullptr;   // shared-memory staging possible (see sh_staging)
+    if (staged) {
         const size_t smem = (size_t)PRE_CAP * p.sh_row_stride_floats * sizeof(float);
-        static PerDeviceOnce once;
-        cudaError_t e = ensure_dynamic_smem(preprocess_fwd_kernel<true>, 200 * 1024, once);
-        if (e != cudaSuccess) return e;
-        preprocess_fwd_kernel<true><<<blocks, PRE_THREADS, smem, stream>>>(p);
+        static PerDeviceOnce once1, once2;
+        if (p.shs_rest) {
+            cudaError_t e = ensure_dynamic_smem(preprocess_fwd_kernel<2>, 200 * 1024, once2);
+            if (e != cudaSuccess) return e;
+            preprocess_fwd_kernel<2><<<blocks, PRE_THREADS, smem, stream>>>(p);
+        } else {
+            cudaError_t e = ensure_dynamic_smem(preprocess_fwd_kernel<1>, 200 * 1024, once1);
+            if (e != cudaSuccess) return e;
+            preprocess_fwd_kernel<1><<<blocks, PRE_THREADS, smem, stream>>>(p);
+        }
     } else {
-        preprocess_fwd_kernel<false><<<blocks, PRE_THREADS, 0, stream>>>(p);
+        preprocess_fwd_kernel<0><<<blocks, PRE_THREADS, 0, stream>>>(p);
     }
     return cudaGetLastError();
 }

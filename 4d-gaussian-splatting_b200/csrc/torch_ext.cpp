@@ -49,9 +49,27 @@ void check(int rc, const char* where) {
 
 }  // namespace
 
-std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
-           torch::Tensor, torch::Tensor, torch::Tensor>
-RasterizeGaussiansCUDA(const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& colors,
+#define FDGS_FWD_PARAMS                                                                                                \
+    const torch::Tensor &background, const torch::Tensor &means3D, const torch::Tensor &colors,                        \
+        const torch::Tensor &flows, const torch::Tensor &opacity, const torch::Tensor &ts, const torch::Tensor &scales, \
+        const torch::Tensor &scales_t, const torch::Tensor &rotations, const torch::Tensor &rotations_r,               \
+        const float scale_modifier, const torch::Tensor &cov3D_precomp, const float prefilter_var,                     \
+        const torch::Tensor &viewmatrix, const torch::Tensor &projmatrix, const float tan_fovx, const float tan_fovy,  \
+        const int image_height, const int image_width, const torch::Tensor &sh, const int degree, const int degree_t,  \
+        const torch::Tensor &campos, const float timestamp, const float time_duration, const bool rot_4d,              \
+        const int gaussian_dim, const bool force_sh_3d, const bool prefiltered, const bool debug
+#define FDGS_FWD_ARGS                                                                                                  \
+    background, means3D, colors, flows, opacity, ts, scales, scales_t, rotations, rotations_r, scale_modifier,         \
+        cov3D_precomp, prefilter_var, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh,       \
+        degree, degree_t, campos, timestamp, time_duration, rot_4d, gaussian_dim, force_sh_3d, prefiltered, debug
+
+using ForwardOut = std::tuple<int, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
+                              torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>;
+
+// sh_rest (possibly empty) / raw_params: the raw-parameter entry of include/fdgs.h (fdgs_forward_args.raw_params)
+static ForwardOut
+forward_impl(const torch::Tensor& sh_rest, const bool raw_params,
+                       const torch::Tensor& background, const torch::Tensor& means3D, const torch::Tensor& colors,
                        const torch::Tensor& flows, const torch::Tensor& opacity, const torch::Tensor& ts,
                        const torch::Tensor& scales, const torch::Tensor& scales_t, const torch::Tensor& rotations,
                        const torch::Tensor& rotations_r, const float scale_modifier, const torch::Tensor& cov3D_precomp,
@@ -92,7 +110,14 @@ RasterizeGaussiansCUDA(const torch::Tensor& background, const torch::Tensor& mea
     fdgs_forward_args a;
     memset(&a, 0, sizeof(a));
     a.P = P; a.D = degree; a.D_t = degree_t;
+    const auto shr_c = contig(sh_rest);
     a.M = (sh.defined() && sh.numel() != 0) ? (int)sh.size(1) : 0;
+    if (shr_c.defined() && shr_c.numel() != 0) {
+        TORCH_CHECK(a.M == 1 && shr_c.dim() == 3 && shr_c.size(0) == P, "fdgs: split SH rows are [P,1,3] + [P,M-1,3]");
+        a.M += (int)shr_c.size(1);
+        a.shs_rest = fptr(shr_c);
+    }
+    a.raw_params = raw_params;
     a.background = fptr(bg_c); a.width = W; a.height = H;
     a.means3D = fptr(means_c); a.shs = fptr(sh_c); a.colors_precomp = fptr(col_c); a.flows_precomp = fptr(flow_c);
     a.opacities = fptr(op_c); a.ts = fptr(ts_c); a.scales = fptr(sc_c); a.scales_t = fptr(sct_c);
@@ -121,16 +146,26 @@ RasterizeGaussiansCUDA(const torch::Tensor& background, const torch::Tensor& mea
                            imgBuffer, covs3D_com, out_means3D);
 }
 
+// the reference's entry point: 30 positional arguments, 11-tuple (rasterize_points.h:18-49)
+ForwardOut RasterizeGaussiansCUDA(FDGS_FWD_PARAMS) { return forward_impl(torch::Tensor(), false, FDGS_FWD_ARGS); }
+
+// raw-parameter entry: the same 30 arguments (scales = log-scales, rotations un-normalised, opacity = logits when
+// raw_params) + the second SH tensor (sh = features_dc [P,1,3], sh_rest = features_rest [P,M-1,3]; may be empty)
+ForwardOut RasterizeGaussiansRaw(FDGS_FWD_PARAMS, const torch::Tensor& sh_rest, const bool raw_params) {
+    return forward_impl(sh_rest, raw_params, FDGS_FWD_ARGS);
+}
+
 namespace {
 struct BackwardOut {
     torch::Tensor dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dflows, dL_dts, dL_dscales,
-        dL_dscales_t, dL_drotations, dL_drotations_r, sh_factors;
+        dL_dscales_t, dL_drotations, dL_drotations_r, sh_factors, dL_dsh_rest;
 };
 }  // namespace
 
 // sh_factor_mode: view-parallel mode -- no dL_dsh rows, the [P,3] colour factors instead (include/fdgs.h: sh_factors)
 static BackwardOut
-backward_impl(const bool sh_factor_mode, const torch::Tensor& background, const torch::Tensor& means3D,
+backward_impl(const bool sh_factor_mode, const torch::Tensor& sh_rest, const bool raw_params,
+                               const torch::Tensor& background, const torch::Tensor& means3D,
                                const torch::Tensor& out_means3D, const torch::Tensor& radii, const torch::Tensor& colors,
                                const torch::Tensor& flows_2d, const torch::Tensor& opacities, const torch::Tensor& ts,
                                const torch::Tensor& scales, const torch::Tensor& scales_t, const torch::Tensor& rotations,
@@ -149,7 +184,8 @@ backward_impl(const bool sh_factor_mode, const torch::Tensor& background, const 
     cudaStream_t stream = c10::cuda::getCurrentCUDAStream().stream();
     const int P = means3D.size(0);
     const int H = dL_dout_color.size(1), W = dL_dout_color.size(2);
-    const int M = (sh.defined() && sh.numel() != 0) ? (int)sh.size(1) : 0;
+    const bool split = sh_rest.defined() && sh_rest.numel() != 0;
+    const int M = ((sh.defined() && sh.numel() != 0) ? (int)sh.size(1) : 0) + (split ? (int)sh_rest.size(1) : 0);
     auto opts = means3D.options().dtype(torch::kFloat32);
 
     // accumulated by the blend kernel -> one zero-filled slab, sliced into the five API tensors
@@ -164,7 +200,8 @@ backward_impl(const bool sh_factor_mode, const torch::Tensor& background, const 
     torch::Tensor dL_dts = torch::empty({P, 1}, opts);
     torch::Tensor dL_dcov3D = torch::empty({P, 6}, opts);
     const bool factors = sh_factor_mode && M > 0;
-    torch::Tensor dL_dsh = factors ? torch::empty({0}, opts) : torch::empty({P, M, 3}, opts);
+    torch::Tensor dL_dsh = factors ? torch::empty({0}, opts) : torch::empty({P, split ? 1 : M, 3}, opts);
+    torch::Tensor dL_dsh_rest = (split && !factors) ? torch::empty({P, M - 1, 3}, opts) : torch::empty({0}, opts);
     torch::Tensor sh_factors = factors ? torch::empty({P, 3}, opts) : torch::empty({0}, opts);
     torch::Tensor dL_dscales = torch::empty({P, 3}, opts);
     torch::Tensor dL_dscales_t = torch::empty({P, 1}, opts);
@@ -201,13 +238,17 @@ backward_impl(const bool sh_factor_mode, const torch::Tensor& background, const 
         a.dL_dflows = dL_dflows.data_ptr<float>(); a.dL_dmean3D = dL_dmeans3D.data_ptr<float>();
         a.dL_dcov3D = dL_dcov3D.data_ptr<float>(); a.dL_dsh = (M > 0 && !factors) ? dL_dsh.data_ptr<float>() : nullptr;
         a.sh_factors = factors ? sh_factors.data_ptr<float>() : nullptr;
+        const auto shr_c = contig(sh_rest);
+        a.shs_rest = split ? fptr(shr_c) : nullptr;
+        a.dL_dsh_rest = (split && !factors) ? dL_dsh_rest.data_ptr<float>() : nullptr;
+        a.raw_params = raw_params;
         a.dL_dts = dL_dts.data_ptr<float>(); a.dL_dscale = dL_dscales.data_ptr<float>();
         a.dL_dscale_t = dL_dscales_t.data_ptr<float>(); a.dL_drot = dL_drotations.data_ptr<float>();
         a.dL_drot_r = dL_drotations_r.data_ptr<float>();
         check(fdgs_backward(&a, (void*)stream), "backward");
     }
     return BackwardOut{dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dflows, dL_dts,
-                       dL_dscales, dL_dscales_t, dL_drotations, dL_drotations_r, sh_factors};
+                       dL_dscales, dL_dscales_t, dL_drotations, dL_drotations_r, sh_factors, dL_dsh_rest};
 }
 
 #define FDGS_BWD_PARAMS                                                                                                \
@@ -232,16 +273,26 @@ backward_impl(const bool sh_factor_mode, const torch::Tensor& background, const 
 std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor,
            torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
 RasterizeGaussiansBackwardCUDA(FDGS_BWD_PARAMS) {
-    BackwardOut o = backward_impl(false, FDGS_BWD_ARGS);
+    BackwardOut o = backward_impl(false, torch::Tensor(), false, FDGS_BWD_ARGS);
     return std::make_tuple(o.dL_dmeans2D, o.dL_dcolors, o.dL_dopacity, o.dL_dmeans3D, o.dL_dcov3D, o.dL_dsh, o.dL_dflows,
                            o.dL_dts, o.dL_dscales, o.dL_dscales_t, o.dL_drotations, o.dL_drotations_r);
 }
 
 // view-parallel variant: same arguments; dL_dsh comes back EMPTY and a 13th tensor holds the [P,3] colour factors
 std::vector<torch::Tensor> RasterizeGaussiansBackwardFactors(FDGS_BWD_PARAMS) {
-    BackwardOut o = backward_impl(true, FDGS_BWD_ARGS);
+    BackwardOut o = backward_impl(true, torch::Tensor(), false, FDGS_BWD_ARGS);
     return {o.dL_dmeans2D, o.dL_dcolors, o.dL_dopacity, o.dL_dmeans3D, o.dL_dcov3D, o.dL_dsh, o.dL_dflows,
             o.dL_dts, o.dL_dscales, o.dL_dscales_t, o.dL_drotations, o.dL_drotations_r, o.sh_factors};
+}
+
+// raw-parameter entry (see RasterizeGaussiansRaw): 14 tensors -- the 12 gradients (w.r.t. the RAW parameters when
+// raw_params; dL_dsh is [P,1,3] when sh_rest is given), the [P,3] colour factors (sh_factor_mode, else empty) and
+// dL_dsh_rest [P,M-1,3] (split rows, else empty)
+std::vector<torch::Tensor> RasterizeGaussiansBackwardRaw(FDGS_BWD_PARAMS, const torch::Tensor& sh_rest, const bool raw_params,
+                                                         const bool sh_factor_mode) {
+    BackwardOut o = backward_impl(sh_factor_mode, sh_rest, raw_params, FDGS_BWD_ARGS);
+    return {o.dL_dmeans2D, o.dL_dcolors, o.dL_dopacity, o.dL_dmeans3D, o.dL_dcov3D, o.dL_dsh, o.dL_dflows,
+            o.dL_dts, o.dL_dscales, o.dL_dscales_t, o.dL_drotations, o.dL_drotations_r, o.sh_factors, o.dL_dsh_rest};
 }
 
 // rebuild + sum the dL_dsh rows of all views from the gathered colour factors (include/fdgs.h: fdgs_sh_outer_sum)
@@ -497,6 +548,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("rasterize_gaussians", &RasterizeGaussiansCUDA);
     m.def("rasterize_gaussians_backward", &RasterizeGaussiansBackwardCUDA);
     m.def("rasterize_gaussians_backward_factors", &RasterizeGaussiansBackwardFactors);
+    m.def("rasterize_gaussians_raw", &RasterizeGaussiansRaw);
+    m.def("rasterize_gaussians_backward_raw", &RasterizeGaussiansBackwardRaw);
     m.def("sh_outer_sum", &ShOuterSum);
     m.def("check_rows_zero", &CheckRowsZero);
     m.def("mark_visible", &markVisible);

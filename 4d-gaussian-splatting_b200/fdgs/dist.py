@@ -307,6 +307,13 @@ class ViewParallelStep:
         assert self.views, "finish(): this rank rendered no view -- pass outer_sum_fn, or give every rank a view"
         rec = self.views[0]
         s, i = rec.settings, rec.inputs
+        if i.get("raw"):
+            # recorded by the raw-parameter entry: the reconstruction kernel takes the activated values (three small
+            # elementwise kernels once per STEP, not per view)
+            act = lambda t, f: f(t) if (t is not None and t.numel()) else t
+            i = dict(i, scales=act(i["scales"], torch.exp), scales_t=act(i["scales_t"], torch.exp),
+                     rotations=act(i["rotations"], torch.nn.functional.normalize),
+                     rotations_r=act(i["rotations_r"], torch.nn.functional.normalize))
         import fdgs
         fdgs.ext().sh_outer_sum(table, stride, meta_off, V, K, slot_of, i["means3D"], i["ts"], i["scales"], i["scales_t"],
                                 i["rotations"], i["rotations_r"], float(s.scale_modifier), float(s.time_duration),

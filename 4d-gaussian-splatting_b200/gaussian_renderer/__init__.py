@@ -10,6 +10,7 @@ CUDA library (fdgs) instead of diff-gaussian-rasterization.
 import the reference's `scene` or `utils` packages, so it also works stand-alone (tests, bench).
 """
 import math
+import os
 
 import torch
 from torch.nn import functional as F
@@ -22,6 +23,46 @@ __all__ = ["render", "GaussianRasterizationSettings", "GaussianRasterizer"]
 
 def _select(mask, *tensors):
     return tuple(None if t is None else t[mask] for t in tensors)
+
+
+def _fused_prologue_ok(pc, pipe, override_color):
+    """Can this frame take the raw-parameter entry (GaussianRasterizer.forward_raw)?  Yes when the model is the
+    reference's GaussianModel in its all-CUDA configuration: raw parameter tensors present, the standard activations
+    (scene/gaussian_model.py:44-60: exp / sigmoid / F.normalize) and no python-side preprocessing or colour override.
+    Then exp, F.normalize x2, sigmoid and the torch.cat of get_features run inside the kernels.  FDGS_FUSED_PROLOGUE=0
+    (or pipe.fused_prologue = False) forces the getter path."""
+    if os.environ.get("FDGS_FUSED_PROLOGUE", "1") == "0" or not getattr(pipe, "fused_prologue", True):
+        return False
+    if override_color is not None or pipe.compute_cov3D_python or pipe.convert_SHs_python:
+        return False
+    need = ["_xyz", "_scaling", "_rotation", "_opacity", "_features_dc", "_features_rest"]
+    if pc.gaussian_dim == 4:
+        need += ["_t", "_scaling_t"]
+    if pc.rot_4d:
+        need += ["_rotation_r"]
+    if not all(isinstance(getattr(pc, n, None), torch.Tensor) for n in need):
+        return False
+    return (getattr(pc, "scaling_activation", None) is torch.exp and getattr(pc, "opacity_activation", None) is torch.sigmoid
+            and getattr(pc, "rotation_activation", None) is F.normalize
+            and pc._features_dc.dim() == 3 and pc._features_dc.shape[1] == 1)
+
+
+def _add_sky(rendered_image, alpha, viewpoint_camera, pc):
+    """sky sphere of radius 60 sampled from the model's environment map (reference: :165-178)"""
+    assert pc.env_map is not None
+    R = 60
+    rays_o, rays_d = viewpoint_camera.get_rays()
+    od = (rays_o * rays_d).sum(-1)
+    dd = (rays_d ** 2).sum(-1)
+    delta = od ** 2 - dd * ((rays_o ** 2).sum(-1) - R ** 2)
+    assert (delta > 0).all()
+    t_inter = -od + torch.sqrt(delta) / dd
+    hit = rays_o + rays_d * t_inter.unsqueeze(-1)
+    tu = torch.atan2(hit[..., 1:2], hit[..., 0:1]) / (2 * torch.pi) + 0.5
+    tv = torch.acos(hit[..., 2:3] / R) / torch.pi
+    texcoord = torch.cat([tu, tv], dim=-1) * 2 - 1
+    sky = F.grid_sample(pc.env_map[None], texcoord[None])[0]
+    return rendered_image + (1 - alpha) * sky
 
 
 def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None):
@@ -62,6 +103,22 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
         debug=pipe.debug,
     )
     rasterizer = GaussianRasterizer(raster_settings=settings)
+
+    if _fused_prologue_ok(pc, pipe, override_color):
+        # raw-parameter entry: no activation kernels, no SH concatenation (reference: :83-91,113-119 and the getters of
+        # scene/gaussian_model.py:179-219)
+        four_d = pc.gaussian_dim == 4
+        rendered_image, radii, depth, alpha, flow, _covs = rasterizer.forward_raw(
+            means3D=xyz, means2D=screenspace_points, opacity_logits=pc._opacity, features_dc=pc._features_dc,
+            features_rest=pc._features_rest if pc._features_rest.numel() else None, log_scales=pc._scaling,
+            rotations_raw=pc._rotation, flow_2d=torch.zeros_like(xyz[:, :2]), ts=pc._t if four_d else None,
+            log_scales_t=pc._scaling_t if four_d else None, rotations_r_raw=pc._rotation_r if pc.rot_4d else None,
+            prefilter_var=pc.prefilter_var if (four_d and pc.prefilter_var > 0.0) else -1.0)
+        assert not env_map_res or pc.env_map is not None
+        if env_map_res:
+            rendered_image = _add_sky(rendered_image, alpha, viewpoint_camera, pc)
+        return {"render": rendered_image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0,
+                "radii": radii, "depth": depth, "alpha": alpha, "flow": flow}
 
     means3D, means2D, opacity = xyz, screenspace_points, pc.get_opacity
     scales = scales_t = rotations = rotations_r = ts = cov3D_precomp = None
@@ -132,21 +189,7 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
         rotations_r=rotations_r, cov3D_precomp=cov3D_precomp, prefilter_var=prefilter_var)
 
     if env_map_res:
-        # sky sphere of radius 60 sampled from the model's environment map (reference: :165-178)
-        assert pc.env_map is not None
-        R = 60
-        rays_o, rays_d = viewpoint_camera.get_rays()
-        od = (rays_o * rays_d).sum(-1)
-        dd = (rays_d ** 2).sum(-1)
-        delta = od ** 2 - dd * ((rays_o ** 2).sum(-1) - R ** 2)
-        assert (delta > 0).all()
-        t_inter = -od + torch.sqrt(delta) / dd
-        hit = rays_o + rays_d * t_inter.unsqueeze(-1)
-        tu = torch.atan2(hit[..., 1:2], hit[..., 0:1]) / (2 * torch.pi) + 0.5
-        tv = torch.acos(hit[..., 2:3] / R) / torch.pi
-        texcoord = torch.cat([tu, tv], dim=-1) * 2 - 1
-        sky = F.grid_sample(pc.env_map[None], texcoord[None])[0]
-        rendered_image = rendered_image + (1 - alpha) * sky
+        rendered_image = _add_sky(rendered_image, alpha, viewpoint_camera, pc)
 
     if mask is not None:
         radii_all = radii.new_zeros(mask.shape)

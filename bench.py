@@ -59,6 +59,10 @@ WORKLOADS = {
     "cfg5": dict(cfg="cfg5", mode="fwdbwd", views=8, metric="fwd+bwd Mpixels/s @1352x1014, 300k 4D Gaussians, 8 views/step",
                  desc="N3V 'flame_steak' shape: 300k 4D Gaussians, duration [0,10], 1352x1014, 8 views per step"),
     "mid": dict(cfg="mid", mode="fwdbwd", views=1, metric="fwd+bwd Mpixels/s", desc="100k 4D Gaussians, 640x480 (smoke)"),
+    # the whole optimisation step around the headline rasterization: render() over a
+    # GaussianModel stand-in holding RAW parameters + photometric loss + backward + Adam
+    "train3": dict(cfg="cfg3", mode="trainstep", views=1, metric="train-step Mpixels/s @1352x1014, 2M 4D Gaussians",
+                   desc="cfg3 scene as a GaussianModel (raw parameters): render() + (0.8 L1 + 0.2 (1-SSIM)) + backward + Adam"),
 }
 
 
@@ -493,6 +497,89 @@ def run_train(args, rank, device):
                     "note": "training loop: ground-truth images resident, loss not read back per step"}}
 
 
+def run_train_step(args, rank, device):
+    """--workload train3: one full optimisation step at the headline size through the reference-facing render().
+    ours     : render() takes the raw-parameter entry (activations + SH concatenation in the kernels), the fused
+               L1 + SSIM loss (fdgs.loss) and the fused multi-tensor Adam (fdgs.optim, dense = torch semantics);
+    reference: the same Python prologue with torch getters (exp / sigmoid / F.normalize / torch.cat), the compiled
+               reference rasterizer, the reference's l1_loss + ssim formula on cuDNN convolutions, torch.optim.Adam."""
+    import helpers
+    import lego
+    from raw_model import RawModel, Pipe
+    cfg, cam, sc, st = helpers.build("cfg3", device=device)
+    cam = cam.to(device)
+    model = RawModel(sc, seed=1, requires_grad=True)
+    g = torch.Generator().manual_seed(5)
+    gt = torch.rand(3, cfg["H"], cfg["W"], generator=g).to(device)
+    bg = torch.zeros(3, device=device)
+    lv = model.leaves()
+    lrs = dict(xyz=1.6e-4, t=1.6e-4, scaling=5e-3, scaling_t=5e-3, rotation=1e-3, rotation_r=1e-3, opacity=5e-2,
+               features_dc=2.5e-3, features_rest=2.5e-3 / 20)     # arguments/__init__.py defaults
+    groups = [{"params": [lv[k]], "lr": lrs[k], "name": k} for k in lv]
+    lam = 0.2
+    if args.impl == "ours":
+        from gaussian_renderer import render
+        from fdgs.loss import l1_ssim_loss
+        from fdgs.optim import FusedAdam
+        opt = FusedAdam(groups, eps=1e-15)
+
+        def one():
+            pkg = render(cam, model, Pipe(), bg)
+            loss = l1_ssim_loss(pkg["render"], gt, lam)
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            return loss
+    else:
+        opt = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+
+        def one():
+            pkg = lego.ref_render(cam, model, bg)
+            img = pkg["render"]
+            loss = (1.0 - lam) * (img - gt).abs().mean() + lam * (1.0 - lego.ssim_torch(img[None], gt[None]))
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            return loss
+
+    last = [None]
+
+    def step():
+        last[0] = one()
+
+    sampler = ClockSampler(int(device.split(":")[1]))
+    sampler.start()
+    ms, wall = timed(step, args.steps, args.warmup, device, 1)
+    clocks = sampler.stop()
+    mpix = cfg["W"] * cfg["H"] / 1e6
+    # phase breakdown (CUDA events around the phases of a few extra steps)
+    phases = {}
+    if args.impl == "ours":
+        from gaussian_renderer import render
+        from fdgs.loss import l1_ssim_loss
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        acc = {"render": 0.0, "loss": 0.0, "backward": 0.0, "adam": 0.0}
+        for _ in range(3):
+            e = [ev() for _ in range(5)]
+            e[0].record(); pkg = render(cam, model, Pipe(), bg)
+            e[1].record(); loss = l1_ssim_loss(pkg["render"], gt, lam)
+            e[2].record(); loss.backward()
+            e[3].record(); opt.step(); opt.zero_grad(set_to_none=True)
+            e[4].record()
+            torch.cuda.synchronize(device)
+            for i, k in enumerate(acc):
+                acc[k] += e[i].elapsed_time(e[i + 1]) / 3
+        phases = acc
+    return {"metric": WORKLOADS["train3"]["metric"], "value": mpix / (ms * 1e-3), "unit": "Mpixels/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "train3: " + WORKLOADS["train3"]["desc"], "lambda_dssim": lam,
+                       "optimizer": "Adam eps 1e-15, 9 parameter groups (dense update)"},
+            "iterations_per_s": 1e3 / ms, "loss": float(last[0]), "phase_ms": phases, "clocks": clocks, "wall_ms_per_step": wall,
+            "e2e": {"value": mpix / (ms * 1e-3), "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "note": "training step: ground-truth image resident, loss not read back per step"}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -537,8 +624,8 @@ def main():
     device = "cuda:%d" % local
     torch.cuda.set_device(device)
 
-    if spec["mode"] == "train":
-        line = run_train(args, rank, device)
+    if spec["mode"] in ("train", "trainstep"):
+        line = run_train(args, rank, device) if spec["mode"] == "train" else run_train_step(args, rank, device)
         if args.impl == "reference":
             line["impl"] = "reference"
             line["config"]["reference"] = "unmodified reference CUDA rasterizer (oracle/_ref/ref_rasterizer.so, sm_100a)"

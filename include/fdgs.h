@@ -94,6 +94,16 @@ typedef struct fdgs_forward_args {
     float* out_depth;      /* [1,H,W]                                          */
     float* out_T;          /* [1,H,W] final transmittance                      */
     int* radii;            /* [P]                                              */
+    /* Raw-parameter entry (version 2).  The reference activates the optimiser's raw
+     * parameters in PyTorch before every render (scene/gaussian_model.py:179-219: exp, sigmoid, F.normalize, and a
+     * torch.cat of features_dc / features_rest); with raw_params != 0 the kernels do it themselves:
+     *   scales, scales_t   are LOG-scales            (exp applied)
+     *   rotations(_r)      are un-normalised         (q / max(||q||, 1e-12))
+     *   opacities          are logits                (sigmoid)
+     * and, independently, a non-NULL shs_rest splits the SH row like the reference model's two tensors:
+     *   shs = features_dc [P,1,3], shs_rest = features_rest [P,M-1,3]  (no 1.15 GB concatenation per frame). */
+    int raw_params;
+    const float* shs_rest;
 } fdgs_forward_args;
 
 /* Scratch handles returned by fdgs_forward (device pointers obtained through
@@ -166,6 +176,13 @@ typedef struct fdgs_backward_args {
      * colour gradient of every Gaussian (zeros where this view did not render it) -- the only view-dependent factor
      * of the rank-one dL_dsh row.  The direction / time terms of the SH backward still go to dL_dmean3D / dL_dts. */
     float* sh_factors;     /* [P,3]   overwritten, or NULL                     */
+    /* Raw-parameter entry, as in fdgs_forward_args: the SAME values as in the forward.  With raw_params != 0 the
+     * gradients dL_dscale, dL_dscale_t, dL_drot, dL_drot_r and dL_dopacity come out w.r.t. the RAW parameters (chain
+     * rule through exp / normalize / sigmoid applied in the kernel).  With shs_rest the SH gradient is split the same
+     * way: dL_dsh = [P,1,3], dL_dsh_rest = [P,M-1,3]. */
+    int raw_params;
+    const float* shs_rest;
+    float* dL_dsh_rest;
 } fdgs_backward_args;
 
 /* Library / build identification. */

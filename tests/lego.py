@@ -98,6 +98,29 @@ def _ref_render(cam, pc, bg_color):
             "depth": depth, "alpha": alpha, "flow": flow}
 
 
+def ssim_torch(img1, img2):
+    """the reference's ssim() (utils/loss_utils.py:39-64) restated: five grouped 11x11 Gaussian convolutions"""
+    import math
+    import torch.nn.functional as F
+    ch = img1.size(-3)
+    g = torch.tensor([math.exp(-(x - 5) ** 2 / float(2 * 1.5 ** 2)) for x in range(11)])
+    g = (g / g.sum()).unsqueeze(1)
+    w = g.mm(g.t()).float().unsqueeze(0).unsqueeze(0).expand(ch, 1, 11, 11).contiguous().to(img1.device)
+    mu1 = F.conv2d(img1, w, padding=5, groups=ch)
+    mu2 = F.conv2d(img2, w, padding=5, groups=ch)
+    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+    s1 = F.conv2d(img1 * img1, w, padding=5, groups=ch) - mu1_sq
+    s2 = F.conv2d(img2 * img2, w, padding=5, groups=ch) - mu2_sq
+    s12 = F.conv2d(img1 * img2, w, padding=5, groups=ch) - mu1_mu2
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    return (((2 * mu1_mu2 + C1) * (2 * s12 + C2)) / ((mu1_sq + mu2_sq + C1) * (s1 + s2 + C2))).mean()
+
+
+def ref_render(cam, pc, bg_color):
+    """public name of _ref_render (bench.py train-step leg)"""
+    return _ref_render(cam, pc, bg_color)
+
+
 def make_optimizer(raw):
     """Adam over the raw parameters with the learning rates of configs/dnerf/lego.yaml:36-44 (eps 1e-15 as
     scene/gaussian_model.py:331-357)."""
