@@ -527,6 +527,15 @@ int fdgs_knn(int n, int k, const float* xyz, char* scratch, int* idx, float* dis
     return FDGS_OK;
 }
 
+int fdgs_debug_activate(int n, const float* log_s, const float* logit, const float* quat, int mode, float* s_out, float* o_out,
+                        float* q_out, void* stream_v) {
+    g_last_error.clear();
+    if (n < 0 || (n > 0 && (!log_s || !logit || !quat || !s_out || !o_out || !q_out))) return fail(FDGS_ERR_INVALID_ARG, "null argument");
+    FDGS_CUDA(fdgs::launch_debug_activate(n, log_s, logit, quat, mode, s_out, o_out, q_out, reinterpret_cast<cudaStream_t>(stream_v)),
+              "debug_activate");
+    return FDGS_OK;
+}
+
 int fdgs_profile_enable(int on) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof_on = on != 0;

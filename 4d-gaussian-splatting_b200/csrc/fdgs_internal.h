@@ -69,6 +69,8 @@ struct PreprocessFwdParams {
     uint4* binrec;          // [P] compact bin record of EVERY Gaussian (see launch_bin_count)
 };
 cudaError_t launch_preprocess_fwd(const PreprocessFwdParams& p, cudaStream_t stream);
+cudaError_t launch_debug_activate(int n, const float* log_s, const float* logit, const float* quat, int mode, float* s_out,
+                                  float* o_out, float* q_out, cudaStream_t stream);
 
 // ---- binning -----------------------------------------------------------------------------------
 // counting sort of the (Gaussian, tile) instances by tile, BIN_CTAS persistent CTAs (binning.cu)

@@ -538,7 +538,22 @@ std::tuple<torch::Tensor, torch::Tensor> Knn(const torch::Tensor& xyz, const int
     return std::make_tuple(idx, d2);
 }
 
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor> DebugActivate(const torch::Tensor& log_s, const torch::Tensor& logit,
+                                                                      const torch::Tensor& quat, const int64_t mode) {
+    const c10::cuda::CUDAGuard guard(log_s.device());
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream().stream();
+    const auto a = log_s.contiguous(), b = logit.contiguous(), q = quat.contiguous();
+    const int n = (int)a.numel();
+    TORCH_CHECK(b.numel() == n && q.numel() == 4 * (int64_t)n, "fdgs: debug_activate shapes");
+    torch::Tensor s = torch::empty_like(a), o = torch::empty_like(b), qo = torch::empty_like(q);
+    check(fdgs_debug_activate(n, a.data_ptr<float>(), b.data_ptr<float>(), q.data_ptr<float>(), (int)mode, s.data_ptr<float>(),
+                              o.data_ptr<float>(), qo.data_ptr<float>(), (void*)stream),
+          "debug_activate");
+    return std::make_tuple(s, o, qo);
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+    m.def("debug_activate", &DebugActivate);
     m.def("l1_ssim_forward", &L1SsimForward);
     m.def("l1_ssim_backward", &L1SsimBackward);
     m.def("adam_step", &AdamStep);

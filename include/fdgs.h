@@ -303,6 +303,11 @@ int fdgs_debug_export_binning(const char* binning_buffer, const char* image_buff
                               unsigned int* n_contrib /*[H*W]*/,
                               void* stream);
 
+/* Test hook of the raw-parameter entry: applies the in-kernel activations to plain arrays of n elements (log_s, logit:
+ * [n]; quat: [n,4]; mode = quaternion-norm summation order, 0 = the library's default). */
+int fdgs_debug_activate(int n, const float* log_s, const float* logit, const float* quat, int mode, float* s_out,
+                        float* o_out, float* q_out, void* stream);
+
 /* Measurement hooks (bench.py): per-stage device time with CUDA events recorded on the launch
  * stream, and a count of the kernels this library launched.  The reference has no equivalent
  * (it times whole iterations from Python, train.py:57-58,89,185). */

@@ -1,34 +1,34 @@
 #!/usr/bin/env python3
-"""Which summation order does ATen's F.normalize use for a [P,4] row norm?  (run under gpurun, once per
-FDGS_NORMALIZE_MODE = 0 / 1 / 2).  Renders the same raw parameters through the getter path (torch activations) and
-through the raw-parameter entry (in-kernel activations) and counts differing words of the conditional covariance --
-zero means the in-kernel exp / normalize are bit-identical to torch's."""
+"""Are the in-kernel activations of the raw-parameter entry bit-identical to torch's?  (run under gpurun)
+exp / sigmoid: one candidate each; F.normalize: three summation orders of the 4-element norm (fdgs_common.cuh)."""
 import os
 import sys
 
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in ("4d-gaussian-splatting_b200", "oracle", "tests"):
-    sys.path.insert(0, os.path.join(ROOT, p))
-import helpers  # noqa: E402
-from raw_model import RawModel, Pipe  # noqa: E402
-from gaussian_renderer import render  # noqa: E402
-from gaussian_renderer.diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "4d-gaussian-splatting_b200"))
+import fdgs  # noqa: E402
 
+C = fdgs.ext()
 dev = "cuda:0"
-cfg, cam, sc, st = helpers.build("mid", device=dev)
-m = RawModel(sc, seed=3)
-r = GaussianRasterizer(GaussianRasterizationSettings(**st))
-with torch.no_grad():
-    z = torch.zeros_like(m._xyz)
-    a = r(means3D=m.get_xyz, means2D=z, opacities=m.get_opacity, shs=m.get_features, flow_2d=z[:, :2].contiguous(), ts=m.get_t,
-          scales=m.get_scaling, scales_t=m.get_scaling_t, rotations=m.get_rotation, rotations_r=m.get_rotation_r)
-    b = r.forward_raw(means3D=m._xyz, means2D=z, opacity_logits=m._opacity, features_dc=m._features_dc,
-                      features_rest=m._features_rest, log_scales=m._scaling, rotations_raw=m._rotation,
-                      flow_2d=z[:, :2].contiguous(), ts=m._t, log_scales_t=m._scaling_t, rotations_r_raw=m._rotation_r)
-vis = a[1] > 0
+g = torch.Generator().manual_seed(1)
+n = 1 << 20
+log_s = (torch.randn(n, generator=g) * 1.5 - 4.0).to(dev)
+logit = (torch.randn(n, generator=g) * 3.0).to(dev)
+quat = (torch.randn(n, 4, generator=g) * (0.2 + 2 * torch.rand(n, 1, generator=g))).to(dev)
 diff = lambda x, y: int((x.contiguous().view(torch.int32) != y.contiguous().view(torch.int32)).sum())
-print("FDGS_NORMALIZE_MODE=%s: cov3D words differing %d of %d, radii differing %d, image words differing %d of %d" % (
-    os.environ.get("FDGS_NORMALIZE_MODE", "0"), diff(a[5][vis], b[5][vis]), int(vis.sum()) * 6, diff(a[1], b[1]),
-    diff(a[0], b[0]), a[0].numel()))
+for mode in (0, 1, 2):
+    s, o, q = C.debug_activate(log_s, logit, quat, mode)
+    qn = torch.nn.functional.normalize(quat)
+    print("mode %d: exp differing %d, sigmoid differing %d, normalize differing %d of %d (max |d| %.3e)" % (
+        mode, diff(s, torch.exp(log_s)), diff(o, torch.sigmoid(logit)), diff(q, qn), 4 * n, float((q - qn).abs().max())))
+# which norm does torch produce?
+nrm = torch.linalg.vector_norm(quat, 2, dim=1)
+x, y, z, w = [quat[:, i].double() for i in range(4)]
+f = lambda t: t.float()
+cands = {"pairwise": f(f(f(x * x) + f(y * y)).double() + f(f(z * z) + f(w * w)).double()),
+         "sequential": f(f(f(f(x * x) + f(y * y)).double() + f(z * z).double()).double() + f(w * w).double()),
+         "exact(double)": f(x * x + y * y + z * z + w * w)}
+for k, v in cands.items():
+    print("vector_norm vs sqrt(%s): differing %d" % (k, diff(nrm, torch.sqrt(v))))
