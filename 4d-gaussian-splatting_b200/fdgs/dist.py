@@ -200,6 +200,14 @@ class ViewParallelStep:
         self.views: List[_ViewRecord] = []
         self._outer_sum_fn = outer_sum_fn
         self.info: Dict[str, object] = {}
+        self.profile = False            # True: CUDA events around the phases of finish() -> info["phase_ms"] (one sync)
+        self._marks = []
+
+    def _mark(self, name):
+        if self.profile and torch.cuda.is_available() and str(self.device).startswith("cuda"):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._marks.append((name, ev))
 
     # ---- installation of the autograd hook (gaussian_renderer/diff_gaussian_rasterization.py) ----
     def __enter__(self):
@@ -230,7 +238,10 @@ class ViewParallelStep:
                views_per_rank: Optional[int] = None) -> ViewBatchStats:
         group, world, P = self.group, _world(self.group), self.P
         st = self.stats
+        self._marks = []
+        self._mark("start")
         st.reduce_radii(group)                                          # union of rendered Gaussians + MAX statistic
+        self._mark("radii_max_allreduce")
         grads = []
         for p in geometry_params:
             if p.grad is None:
@@ -248,6 +259,7 @@ class ViewParallelStep:
         idx = torch.nonzero(mask).squeeze(1)                            # host sync: K sizes the buffers
         K = int(idx.numel())
         sparse_ok = int(bad.item()) == 0 and K <= self.dense_above * P
+        self._mark("union_index_build")
         self.info = {"K": K, "union_fraction": K / max(P, 1), "geometry_path": "rows" if sparse_ok else "dense",
                      "views_local": len(self.views)}
 
@@ -257,8 +269,12 @@ class ViewParallelStep:
             if sparse_ok:
                 if K > 0:
                     flat = _pack(bucket, idx)
+                    self._mark("geometry_pack")
                     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+                    self._mark("geometry_allreduce")
                     _unpack(flat, bucket, idx)
+                    self._mark("geometry_unpack")
+                    self.info["geometry_allreduce_bytes"] = int(flat.numel() * 4)
             else:
                 works = [dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group, async_op=True) for g in bucket]
                 for w in works:
@@ -282,9 +298,11 @@ class ViewParallelStep:
                     torch.index_select(rec.factors, 0, idx, out=local[v, :3 * K].view(K, 3))
                 local[v, meta_off] = rec.timestamp
                 local[v, meta_off + 1:meta_off + 4] = rec.campos.reshape(3).to(local.dtype)
+            self._mark("factor_pack")
             if world > 1:
                 table = torch.empty(world * views_per_rank, stride, dtype=torch.float32, device=union.device)
                 dist.all_gather_into_tensor(table, local, group=group)
+                self._mark("factor_allgather")
             else:
                 table = local
             slot_of = torch.where(mask, torch.cumsum(mask.to(torch.int32), 0, dtype=torch.int32) - 1,
@@ -295,8 +313,12 @@ class ViewParallelStep:
                     p.grad = torch.empty_like(p)
                 outs.append(p.grad)
             self._outer_sum(table, stride, meta_off, table.shape[0], K, slot_of, outs)
+            self._mark("sh_outer_sum")
             self.info.update(views_total=int(table.shape[0]), factor_bytes_per_rank=int(local.numel() * 4))
         self.views = []
+        if self._marks:
+            torch.cuda.synchronize()
+            self.info["phase_ms"] = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(self._marks[:-1], self._marks[1:])}
         return st
 
     def _outer_sum(self, table, stride, meta_off, V, K, slot_of, outs):

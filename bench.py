@@ -8,7 +8,8 @@ backward of a view of the synthetic scene of SURVEY.md section 8(d), through the
 
   value   inputs resident in HBM, CUDA events, K steps after W warm-ups, max over ranks
   e2e     same call with HOST buffers: per step the camera matrices and the upstream gradient image are copied
-          host->device from pinned memory (the image on a copy stream, overlapping the forward, both arms alike) and
+          host->device from pinned memory (the image on a copy stream, double-buffered and issued one step ahead like a
+          prefetching data loader, both arms alike) and
           the loss is read back device->host (asynchronously into pinned memory, collected one step later and before
           the clock stops, so the launch queue never drains)
   N > 1   one view per rank (weak scaling), replicated Gaussians; the gradient exchange of fdgs/dist.py inside the
@@ -213,6 +214,14 @@ class Runner:
         self.exchange = impl == "ours" and self.backward and (world > 1 or len(wl.view_ids) > 1) and \
             os.environ.get("FDGS_DENSE_ALLREDUCE") is None
         self.exchange_info = None
+        self.profile_exchange = False
+        # e2e leg: the upstream gradient image of a view is double-buffered on the device and uploaded one step ahead
+        # on the copy stream (a data loader prefetching the next ground-truth image); every step still copies its
+        # inputs host->device inside the timed region
+        self.g_buf = [[torch.empty_like(g, device=wl.device) for _ in range(2)] for g in wl.G_host] if self.backward else []
+        self.g_ready = [[None, None] for _ in wl.G_host]
+        self.g_used = [[None, None] for _ in wl.G_host]
+        self.g_step = 0
 
     def _raster(self, settings):
         p, sc = self.wl.params, self.wl.scene
@@ -241,6 +250,7 @@ class Runner:
         if self.exchange:
             from fdgs.dist import ViewParallelStep
             step = ViewParallelStep(wl.P, wl.device)
+            step.profile = self.profile_exchange
             step.__enter__()
         result = None
         try:
@@ -252,19 +262,25 @@ class Runner:
                     for k, h in wl.cam_host[i].items():
                         st[k] = h.to(wl.device, non_blocking=True)
                     if self.backward:
-                        # the upstream gradient image (stand-in for the ground-truth image of a training step) is
-                        # uploaded on a copy stream while the forward runs, like a data loader prefetching the view
-                        with torch.cuda.stream(self.copy_stream):
-                            G = wl.G_host[i].to(wl.device, non_blocking=True)
-                            ready = torch.cuda.Event()
-                            ready.record(self.copy_stream)
+                        # the upstream gradient image (stand-in for the ground-truth image of a training step): uploaded
+                        # on a copy stream, this step's copy was issued during the previous step (prefetch depth 1)
+                        b = self.g_step & 1
+                        if self.g_ready[i][b] is None:
+                            self._upload(i, b)
+                        G, ready = self.g_buf[i][b], self.g_ready[i][b]
+                        self.g_ready[i][b] = None
                 if self.backward:
                     (color, radii, depth, alpha, flow, covs), means2D = self._raster(st)
                     if host_inputs:
                         cur.wait_event(ready)
-                        G.record_stream(cur)
                     loss = (color * G).sum() / self.views_total
                     loss.backward()
+                    if host_inputs:
+                        b = self.g_step & 1
+                        ev = torch.cuda.Event()
+                        ev.record(cur)
+                        self.g_used[i][b] = ev          # the buffer may be overwritten once this step's kernels are done
+                        self._upload(i, b ^ 1)          # next step's image, overlapping the rest of this step
                     result = loss.detach() if result is None else result + loss.detach()
                     if step is not None:
                         step.add_view_stats(means2D.grad, radii)
@@ -288,6 +304,7 @@ class Runner:
             stats.reduce()
             allreduce_gradients([v.grad for v in wl.params.values()])
         if host_inputs:
+            self.g_step += 1
             # device->host read of the step's result: an asynchronous copy into pinned memory, collected at the start of
             # the next step (and by drain() before the clock stops) -- the way a training loop logs its loss without
             # stalling the launch queue.  Every step's result is read inside the timed region.
@@ -297,6 +314,15 @@ class Runner:
             self.pending = True
             return prev
         return result
+
+    def _upload(self, i, b):
+        with torch.cuda.stream(self.copy_stream):
+            if self.g_used[i][b] is not None:
+                self.copy_stream.wait_event(self.g_used[i][b])
+            self.g_buf[i][b].copy_(self.wl.G_host[i], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self.g_ready[i][b] = ev
 
     def drain(self):
         """Wait for and return the most recent step's result (None if nothing is pending)."""
@@ -559,6 +585,8 @@ def run_train_step(args, rank, device):
         from fdgs.loss import l1_ssim_loss
         ev = lambda: torch.cuda.Event(enable_timing=True)
         acc = {"render": 0.0, "loss": 0.0, "backward": 0.0, "adam": 0.0}
+        import fdgs
+        fdgs.profile_enable(True)
         for _ in range(3):
             e = [ev() for _ in range(5)]
             e[0].record(); pkg = render(cam, model, Pipe(), bg)
@@ -569,6 +597,9 @@ def run_train_step(args, rank, device):
             torch.cuda.synchronize(device)
             for i, k in enumerate(acc):
                 acc[k] += e[i].elapsed_time(e[i + 1]) / 3
+        prof = fdgs.profile_read()
+        fdgs.profile_enable(False)
+        acc["rasterizer_stage_ms"] = {k: (v[0] / max(v[1], 1)) for k, v in prof.items() if v[1] > 0}
         phases = acc
     return {"metric": WORKLOADS["train3"]["metric"], "value": mpix / (ms * 1e-3), "unit": "Mpixels/s", "n_gpus": 1,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -679,6 +710,22 @@ def main():
         torch.cuda.synchronize(device)
         prof = fdgs.profile_read()
         fdgs.profile_enable(False)
+        if runner.exchange:
+            # phase table of the gradient exchange (CUDA events inside ViewParallelStep.finish, 3 extra steps)
+            runner.profile_exchange = True
+            acc = {}
+            for _ in range(3):
+                runner.step(False)
+                for k, v in (runner.exchange_info.get("phase_ms") or {}).items():
+                    acc[k] = acc.get(k, 0.0) + v / 3
+            runner.profile_exchange = False
+            runner.exchange_info = dict(runner.exchange_info, phase_ms=acc)
+            n = eff_world
+            ab, gb = runner.exchange_info.get("geometry_allreduce_bytes"), runner.exchange_info.get("factor_bytes_per_rank")
+            if n > 1 and ab and acc.get("geometry_allreduce"):
+                runner.exchange_info["geometry_allreduce_busbw_GBps"] = ab * 2 * (n - 1) / n / (acc["geometry_allreduce"] * 1e-3) / 1e9
+            if n > 1 and gb and acc.get("factor_allgather"):
+                runner.exchange_info["factor_allgather_busbw_GBps"] = gb * (n - 1) / (acc["factor_allgather"] * 1e-3) / 1e9
         stage_ms = {k: (v[0] / max(v[1], 1)) for k, v in prof.items() if v[1] > 0}   # per view
         C = fdgs.ext()
         with torch.no_grad():

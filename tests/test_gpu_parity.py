@@ -64,11 +64,11 @@ def check_grad_vs_reference(gname, a, runs):
         return
     l2 = ((a.double() - m).norm() / nm).item()
     err = (a.double() - m).abs().max().item() / sc
-    if l2n < 1e-3:
+    if l2n < 2e-4:
         assert l2 < max(1e-4, 2.5 * l2n), (gname, "l2", l2, "ref spread", l2n)
         assert err < max(1e-4, 3 * mxn), (gname, "max", err, "ref spread", mxn)
     else:
-        # The reference does not reproduce ITSELF to 0.1 % here (cfg5's long time axis: a handful of Gaussians with
+        # The reference does not reproduce ITSELF to 0.02 % here (cfg5's long time axis: a handful of Gaussians with
         # near-singular conditional covariances carry most of the norm and amplify the atomics' rounding noise to
         # 5-30 %, profiles/r02_parity_table.md).  Norms are then heavy-tailed statistics of a few rows: keep a loose
         # norm bound and check the well-conditioned majority row by row instead.

@@ -182,3 +182,21 @@ def test_rigid_loss_with_grid_knn_matches_brute_force():
         vd = torch.norm(vel[idx] - vel[None, :, None], p=2, dim=-1)
         out.append((weight * vd).sum() / k / n)
     assert float(out[0]) == float(out[1]) and float(out[0]) > 0
+
+
+def test_dist_cuda2_equals_exact_three_nearest():
+    """simple-knn's distCUDA2 (simple-knn/simple_knn.cu:139-178): mean squared distance to the 3 nearest other points"""
+    from fdgs.knn import distCUDA2
+    g = torch.Generator().manual_seed(21)
+    x = torch.rand(3000, 3, generator=g) * 2.6 - 1.3
+    x[10] = x[4]                                             # an exact duplicate: distance 0 counts, the point itself does not
+    xd = x.to(DEV)
+    got = distCUDA2(xd).cpu().numpy()
+    xn = x.numpy().astype(np.float32)
+    d = xn[:, None, :] - xn[None, :, :]
+    d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+    np.fill_diagonal(d2, np.inf)
+    best = np.sort(d2, axis=1)[:, :3]
+    want = (best[:, 0] + best[:, 1] + best[:, 2]) / np.float32(3.0)
+    assert np.allclose(got, want, rtol=1e-6, atol=0)
+    assert got[10] <= got.mean() and np.isfinite(got).all()

@@ -32,3 +32,19 @@ cands = {"pairwise": f(f(f(x * x) + f(y * y)).double() + f(f(z * z) + f(w * w)).
          "exact(double)": f(x * x + y * y + z * z + w * w)}
 for k, v in cands.items():
     print("vector_norm vs sqrt(%s): differing %d" % (k, diff(nrm, torch.sqrt(v))))
+
+# more candidates for the 4-element sum of squares, emulated in double (products of floats are exact in double)
+X = [quat[:, i].double() for i in range(4)]
+sq = [v * v for v in X]
+fl = lambda t: t.float().double()
+import itertools
+cand = {}
+for perm in itertools.permutations(range(4)):
+    a, b, c, d = perm
+    cand["fma-chain %s" % (perm,)] = fl(fl(fl(fl(sq[a]) + sq[b]) + sq[c]) + sq[d])
+    cand["seq %s" % (perm,)] = fl(fl(fl(fl(sq[a]) + fl(sq[b])) + fl(sq[c])) + fl(sq[d]))
+    cand["pair-fma %s" % (perm,)] = fl(fl(fl(sq[a]) + sq[b]) + fl(fl(sq[c]) + sq[d]))
+best = sorted(((diff(nrm, torch.sqrt(v.float())), k) for k, v in cand.items()))[:6]
+print("closest candidates to torch.linalg.vector_norm:", best)
+n2 = (quat * quat).sum(1)
+print("vector_norm vs sqrt((q*q).sum(1)): differing", diff(nrm, torch.sqrt(n2)))
