@@ -287,9 +287,13 @@ static_assert(sizeof(InstRec) == 64, "InstRec must be 64 bytes");
 // 61 M of the ~110-190 M shared-memory wavefronts of each blend kernel); with an 80-byte stride 8 consecutive
 // records cover all 32 banks (20 j mod 32 = 0, 20, 8, 28, 16, 4, 24, 12) and the loads are conflict-free.  The
 // extra 16 bytes per instance are HBM traffic the blend kernels, at < 8 % of DRAM bandwidth, do not feel.
+// pad.x (as bits): CULL MASK -- bit w set = the instance may contribute to warp w's 8x4 pixel rectangle of its tile
+// (warps tile the 16x16 block 2 wide by 4 high; rect_may_contribute below), evaluated ONCE per instance when the
+// record is written (binning.cu: tile_sort_kernel) instead of once per warp and per blend pass.
 struct __align__(16) StageRec {
     float4 q0, q1, q2, q3, pad;
 };
+constexpr int kWarpRectW = 8, kWarpRectH = 4;   // pixel footprint of one warp of the blend kernels
 static_assert(sizeof(StageRec) == 80, "StageRec must be 80 bytes");
 constexpr uint32_t kStageRecBytes = 80u;
 
@@ -312,6 +316,11 @@ __device__ __forceinline__ bool rect_may_contribute(float x0, float y0, float A,
     const float q2 = 0.5f * (A * tx * tx + C * ddy * ddy) + B * tx * ddy;
     // if the centre is outside in one axis only, only that axis' edge applies; inside: q = 0
     float qmin = (ddx != 0.f) ? ((ddy != 0.f) ? fminf(q1, q2) : q1) : ((ddy != 0.f) ? q2 : 0.f);
+    // thin, rotated Gaussians far from their centre: the three terms of q are large and cancel, their fp32 rounding
+    // error can exceed the slack -> never cull on such a value (the blend loop decides those pairs exactly)
+    const float mag = fmaxf(fabsf(A * ddx * ddx) + fabsf(C * ty * ty) + 2.f * fabsf(B * ddx * ty),
+                            fabsf(A * tx * tx) + fabsf(C * ddy * ddy) + 2.f * fabsf(B * tx * ddy));
+    if (!(mag < 128.f) && pmin < 3.0e38f) return true;
     return !(qmin > -pmin + 1e-3f);   // also true for pmin = -inf, false for pmin = +inf
 }
 
@@ -370,6 +379,17 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() {
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// 4-byte asynchronous global -> shared copy (SASS: LDGSTS): no register staging, any 4-byte alignment -- used for the
+// split SH rows (12-byte + 564-byte pieces) that the bulk-copy engine cannot address
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// One split SH row (3 floats at dc, row_floats - 3 at rest) -> dst[0 .. row_floats), by the 32 lanes of a warp
+__device__ __forceinline__ void split_row_to_smem(float* dst, const float* __restrict__ dc, const float* __restrict__ rest,
+                                                  int row_floats, int lane) {
+    for (int f = lane; f < row_floats; f += 32) cp_async4(dst + f, (f < 3) ? dc + f : rest + (f - 3));
 }
 // make generic-proxy smem writes visible to the async proxy before a bulk store reads them
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -252,16 +252,15 @@ __global__ void __launch_bounds__(SB_THREADS, 6) sh_bwd_kernel(const PreprocessB
             a.sh_factors[3 * idx + 2] = 0.f;
         }
     } else if (a.dL_dsh_rest != nullptr) {
-        // split gradient tensors: [P,1,3] and [P,M-1,3]
+        // split gradient tensors: [P,1,3] and [P,M-1,3]; a warp per non-rendered row
         const int rows_here = min(SB_THREADS, a.P - blockIdx.x * SB_THREADS);
         const size_t r0 = (size_t)blockIdx.x * SB_THREADS;
         const int rest_floats = row_floats - 3;
-        for (int f = tid; f < rows_here * row_floats; f += SB_THREADS) {
-            const int r = f / row_floats, c = f - r * row_floats;
-            if (slot_of[r] < 0) {
-                if (c < 3) a.dL_dsh[(r0 + r) * 3 + c] = 0.f;
-                else a.dL_dsh_rest[(r0 + r) * rest_floats + (c - 3)] = 0.f;
-            }
+        for (int r = warp; r < rows_here; r += SB_THREADS / 32) {
+            if (slot_of[r] >= 0) continue;
+            if (lane < 3) a.dL_dsh[(r0 + r) * 3 + lane] = 0.f;
+            float* rest = a.dL_dsh_rest + (r0 + r) * rest_floats;
+            for (int f = lane; f < rest_floats; f += 32) rest[f] = 0.f;
         }
     } else {
         const int rows_here = min(SB_THREADS, a.P - blockIdx.x * SB_THREADS);
@@ -309,12 +308,12 @@ __global__ void __launch_bounds__(SB_THREADS, 6) sh_bwd_kernel(const PreprocessB
             } else {
                 if (mine) slot_idx[my_rank - lo] = idx;
                 __syncthreads();
-                for (int sidx = 0; sidx < cnt; ++sidx) {
+                for (int sidx = warp; sidx < cnt; sidx += SB_THREADS / 32) {
                     const size_t g = (size_t)slot_idx[sidx];
-                    float* dst = rows + (size_t)sidx * a.sh_row_stride_floats;
-                    for (int f = tid; f < row_floats; f += SB_THREADS)
-                        dst[f] = (f < 3) ? __ldg(a.shs + g * 3 + f) : __ldg(a.shs_rest + g * rest_floats + (f - 3));
+                    split_row_to_smem(rows + (size_t)sidx * a.sh_row_stride_floats, a.shs + g * 3, a.shs_rest + g * rest_floats,
+                                      row_floats, lane);
                 }
+                cp_async_wait_all();
                 __syncthreads();
             }
             if (mine) {
@@ -335,13 +334,12 @@ __global__ void __launch_bounds__(SB_THREADS, 6) sh_bwd_kernel(const PreprocessB
             if (SPLIT && !FACTORS) {
                 // the gradient rows, now in the slots, go out the way the rows came in: coalesced, split over the two tensors
                 __syncthreads();
-                for (int sidx = 0; sidx < cnt; ++sidx) {
+                for (int sidx = warp; sidx < cnt; sidx += SB_THREADS / 32) {
                     const size_t g = (size_t)slot_idx[sidx];
                     const float* src = rows + (size_t)sidx * a.sh_row_stride_floats;
-                    for (int f = tid; f < row_floats; f += SB_THREADS) {
-                        if (f < 3) a.dL_dsh[g * 3 + f] = src[f];
-                        else a.dL_dsh_rest[g * rest_floats + (f - 3)] = src[f];
-                    }
+                    if (lane < 3) a.dL_dsh[g * 3 + lane] = src[lane];
+                    float* rest = a.dL_dsh_rest + g * rest_floats;
+                    for (int f = lane; f < rest_floats; f += 32) rest[f] = src[f + 3];
                 }
             }
         }

@@ -374,16 +374,16 @@ __global__ void __launch_bounds__(PRE_THREADS, 5) preprocess_fwd_kernel(const Pr
                         mbar_wait(&bar, (uint32_t)round & 1u);
                     }
                 } else {
-                    // split rows: every thread of the CTA copies, row by row, coalesced 4-byte words
+                    // split rows: a warp per row, asynchronous 4-byte copies (LDGSTS) -- all rows of the round in flight at once
                     if (mine) slot_idx[my_rank - lo] = idx;
                     __syncthreads();
                     const int rest_floats = row_floats - 3;
-                    for (int sidx = 0; sidx < cnt; ++sidx) {
+                    for (int sidx = threadIdx.x >> 5; sidx < cnt; sidx += PRE_THREADS / 32) {
                         const size_t g = (size_t)slot_idx[sidx];
-                        float* dst = rows + (size_t)sidx * stride;
-                        for (int f = threadIdx.x; f < row_floats; f += PRE_THREADS)
-                            dst[f] = (f < 3) ? __ldg(a.shs + g * 3 + f) : __ldg(a.shs_rest + g * rest_floats + (f - 3));
+                        split_row_to_smem(rows + (size_t)sidx * stride, a.shs + g * 3, a.shs_rest + g * rest_floats, row_floats,
+                                          threadIdx.x & 31);
                     }
+                    cp_async_wait_all();
                     __syncthreads();
                 }
                 if (mine) eval(RowSmem{reinterpret_cast<const float4*>(slot)});

