@@ -313,7 +313,7 @@ __device__ __forceinline__ void gather_records(const uint32_t* ids /* shared or 
     float4* dst = reinterpret_cast<float4*>(recs);   // 5 float4 per staged record, the fifth is padding
     // thread q writes the q-th float4 of the tile's output stream: fully coalesced stores; 4 of every 5
     // consecutive threads read the 4 planes of one gathered record (one 64-byte line)
-    const int total = 5 * n;   // the fifth float4 of a staged record (cull mask + padding) is written by write_cull_masks
+    const int total = 5 * n;
     for (int q0 = threadIdx.x; q0 < total; q0 += 4 * THREADS) {
         float4 v[4];
 #pragma unroll
@@ -328,43 +328,8 @@ __device__ __forceinline__ void gather_records(const uint32_t* ids /* shared or 
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int q = q0 + u * THREADS;
-            if (q < total && (q % 5) != 4) dst[q] = v[u];
+            if (q < total) dst[q] = v[u];
         }
-    }
-}
-
-// The cull mask of every instance of one tile (StageRec::pad.x): which of the tile's eight 8x4 warp rectangles can the
-// instance's alpha >= 1/255 footprint reach?  Exactly the test the blend kernels used to run per warp and per pass
-// (fdgs_common.cuh: rect_may_contribute), so the set of (warp, instance) pairs they walk is unchanged.  A cheap
-// conservative bounding-box test (half extents of the footprint ellipse) rejects most rectangles before the exact one.
-template <int THREADS>
-__device__ __forceinline__ void write_cull_masks(const uint32_t* ids, int n, const InstRec* __restrict__ grec,
-                                                 StageRec* __restrict__ recs, int tile_x, int tile_y) {
-    const float4* src = reinterpret_cast<const float4*>(grec);
-    for (int i = threadIdx.x; i < n; i += THREADS) {
-        const size_t g = ids[i];
-        const float4 a = __ldg(src + g * 4 + 0);   // x, y, pmin, id
-        const float4 c = __ldg(src + g * 4 + 1);   // A, B, C, opacity
-        const float4 e = __ldg(src + g * 4 + 3);   // flow, -B/C, -B/A
-        // footprint q(d) <= -pmin + slack: |dx| <= sqrt(2 qmax C / det), |dy| <= sqrt(2 qmax A / det)
-        float ex = INFINITY, ey = INFINITY;
-        const float det = c.x * c.z - c.y * c.y;
-        const float qmax = -a.z + 2e-3f;
-        if (a.z > -3.0e38f && a.z < 3.0e38f && det > 0.f && qmax > 0.f) {
-            ex = sqrtf(2.f * qmax * c.z / det) * 1.001f + 1e-3f;
-            ey = sqrtf(2.f * qmax * c.x / det) * 1.001f + 1e-3f;
-        }
-        uint32_t mask = 0u;
-        if (!(a.z >= 3.0e38f)) {   // pmin = +inf: never contributes
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                const float bx0 = (float)(tile_x * TILE_X + (w & 1) * kWarpRectW), bx1 = bx0 + (float)(kWarpRectW - 1);
-                const float by0 = (float)(tile_y * TILE_Y + (w >> 1) * kWarpRectH), by1 = by0 + (float)(kWarpRectH - 1);
-                const bool box = !(a.x + ex < bx0 || a.x - ex > bx1 || a.y + ey < by0 || a.y - ey > by1);   // NaN extents: true
-                if (box && rect_may_contribute(a.x, a.y, c.x, c.y, c.z, a.z, e.z, e.w, bx0, bx1, by0, by1)) mask |= 1u << w;
-            }
-        }
-        reinterpret_cast<float4*>(recs + i)[4] = make_float4(__uint_as_float(mask), 0.f, 0.f, 0.f);
     }
 }
 
@@ -409,10 +374,9 @@ constexpr int SORT_LARGE_THREADS = 1024, SORT_LARGE_KEYS = 16384;    // 139 KB o
 template <bool LARGE>
 __global__ void __launch_bounds__(LARGE ? SORT_LARGE_THREADS : SORT_SMALL_THREADS)
 tile_sort_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ keys, uint32_t* __restrict__ point_list,
-                 const InstRec* __restrict__ grec, StageRec* __restrict__ recs, int grid_x) {
+                 const InstRec* __restrict__ grec, StageRec* __restrict__ recs) {
     extern __shared__ uint64_t skeys[];
     const uint2 range = ranges[blockIdx.x];
-    const int tile_y = blockIdx.x / grid_x, tile_x = blockIdx.x - tile_y * grid_x;
     const int n = (int)(range.y - range.x);
     if (n <= 0) return;
     uint64_t* gk = keys + range.x;
@@ -421,19 +385,16 @@ tile_sort_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ keys, 
         if (n > SORT_SMALL_KEYS) return;
         block_merge_sort<SORT_SMALL_THREADS, 8>(skeys, gk, n, ids);
         gather_records<SORT_SMALL_THREADS>(reinterpret_cast<const uint32_t*>(skeys), n, grec, recs + range.x);
-        write_cull_masks<SORT_SMALL_THREADS>(reinterpret_cast<const uint32_t*>(skeys), n, grec, recs + range.x, tile_x, tile_y);
     } else {
         if (n <= SORT_SMALL_KEYS) return;
         if (n <= SORT_LARGE_KEYS) {
             block_merge_sort<SORT_LARGE_THREADS, 16>(skeys, gk, n, ids);
             gather_records<SORT_LARGE_THREADS>(reinterpret_cast<const uint32_t*>(skeys), n, grec, recs + range.x);
-            write_cull_masks<SORT_LARGE_THREADS>(reinterpret_cast<const uint32_t*>(skeys), n, grec, recs + range.x, tile_x, tile_y);
         } else {
             bitonic_sort(gk, n, threadIdx.x, SORT_LARGE_THREADS);
             for (int i = threadIdx.x; i < n; i += SORT_LARGE_THREADS) ids[i] = (uint32_t)(gk[i] & 0xffffffffu);
             __syncthreads();
             gather_records<SORT_LARGE_THREADS>(ids, n, grec, recs + range.x);
-            write_cull_masks<SORT_LARGE_THREADS>(ids, n, grec, recs + range.x, tile_x, tile_y);
         }
     }
 }
@@ -514,17 +475,17 @@ cudaError_t launch_bin_scatter(int P, const uint4* binrec, int grid_x, int grid_
 
 int tile_sort_pack_kernel_count(int max_count) { return max_count > SORT_SMALL_KEYS ? 2 : 1; }
 
-cudaError_t launch_tile_sort_pack(int num_tiles, int grid_x, int max_count, int R, const uint2* ranges, uint64_t* keys,
+cudaError_t launch_tile_sort_pack(int num_tiles, int max_count, int R, const uint2* ranges, uint64_t* keys,
                                   const InstRec* grec, StageRec* recs, uint32_t* point_list, cudaStream_t stream) {
     if (num_tiles <= 0 || R <= 0) return cudaSuccess;
     constexpr size_t small_smem = (size_t)(SORT_SMALL_KEYS + SORT_SMALL_KEYS / 8) * sizeof(uint64_t);
     constexpr size_t large_smem = (size_t)(SORT_LARGE_KEYS + SORT_LARGE_KEYS / 16) * sizeof(uint64_t);
-    tile_sort_kernel<false><<<num_tiles, SORT_SMALL_THREADS, small_smem, stream>>>(ranges, keys, point_list, grec, recs, grid_x);
+    tile_sort_kernel<false><<<num_tiles, SORT_SMALL_THREADS, small_smem, stream>>>(ranges, keys, point_list, grec, recs);
     if (max_count > SORT_SMALL_KEYS) {
         static PerDeviceOnce once;
         cudaError_t e = ensure_dynamic_smem(tile_sort_kernel<true>, (int)large_smem, once);
         if (e != cudaSuccess) return e;
-        tile_sort_kernel<true><<<num_tiles, SORT_LARGE_THREADS, large_smem, stream>>>(ranges, keys, point_list, grec, recs, grid_x);
+        tile_sort_kernel<true><<<num_tiles, SORT_LARGE_THREADS, large_smem, stream>>>(ranges, keys, point_list, grec, recs);
     }
     return cudaGetLastError();
 }

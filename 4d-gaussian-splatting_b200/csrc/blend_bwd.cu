@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(BB_THREADS, AUX ? 3 : 4) blend_bwd_kernel(cons
     const int pix_x = wx0 + (lane & 7), pix_y = wy0 + (lane >> 3);
     const bool inside = pix_x < p.W && pix_y < p.H;
     const float pxf = (float)pix_x, pyf = (float)pix_y;
+    const float bx0 = (float)wx0, bx1 = (float)(wx0 + 7), by0 = (float)wy0, by1 = (float)(wy0 + 3);
     const int HW = p.H * p.W;
     const int pix_id = pix_y * p.W + pix_x;
 
@@ -139,7 +140,13 @@ __global__ void __launch_bounds__(BB_THREADS, AUX ? 3 : 4) blend_bwd_kernel(cons
             const StageRec* st = sm.recs[s];
             for (int r0 = ((cnt - 1) >> 5) << 5; r0 >= 0; r0 -= 32) {
                 const int j = r0 + lane;
-                const bool rel = (j < cnt) && ((unsigned)(lo + j) < wmax) && ((__float_as_uint(st[j].pad.x) >> warp) & 1u);
+                bool rel = false;
+                if (j < cnt && (unsigned)(lo + j) < wmax) {
+                    const float4 a = st[j].q0;
+                    const float4 c = st[j].q1;
+                    const float4 e = st[j].q3;
+                    rel = rect_may_contribute(a.x, a.y, c.x, c.y, c.z, a.z, e.z, e.w, bx0, bx1, by0, by1);
+                }
                 uint32_t m = __ballot_sync(0xffffffffu, rel);
                 while (m) {
                     const int k = 31 - __clz(m);
@@ -371,6 +378,7 @@ __global__ void __launch_bounds__(B2_THREADS, ACOL_SMEM ? 4 : 3) blend_bwd2_kern
     const int pix_x = wx0 + (lane & 7), pix_y = wy0 + (lane >> 3);
     const bool inside = pix_x < p.W && pix_y < p.H;
     const float pxf = (float)pix_x, pyf = (float)pix_y;
+    const float bx0 = (float)wx0, bx1 = (float)(wx0 + 7), by0 = (float)wy0, by1 = (float)(wy0 + 3);
     const float rcx = (float)wx0 + 3.5f, rcy = (float)wy0 + 1.5f;            // rectangle centre
     const float u = (float)(lane & 7) - 3.5f, v = (float)(lane >> 3) - 1.5f;   // this pixel's offset from it
     const int HW = p.H * p.W;
@@ -512,12 +520,17 @@ __global__ void __launch_bounds__(B2_THREADS, ACOL_SMEM ? 4 : 3) blend_bwd2_kern
             const StageRec* st = sm.recs[s];
             for (int r0 = ((cnt - 1) >> 5) << 5; r0 >= 0; r0 -= 32) {
                 const int j = r0 + lane;
-                // cull mask written with the record (binning.cu: write_cull_masks)
-                const bool rel = (j < cnt) && ((unsigned)(lo + j) < wmax) && ((__float_as_uint(st[j].pad.x) >> warp) & 1u);
+                bool rel = false;
+                float4 a, c, e;
+                if (j < cnt && (unsigned)(lo + j) < wmax) {
+                    a = st[j].q0;
+                    c = st[j].q1;
+                    e = st[j].q3;
+                    rel = rect_may_contribute(a.x, a.y, c.x, c.y, c.z, a.z, e.z, e.w, bx0, bx1, by0, by1);
+                }
                 const uint32_t m = __ballot_sync(0xffffffffu, rel);
                 if (m == 0u) continue;
                 if (rel) {
-                    const float4 a = st[j].q0, c = st[j].q1;
                     // back-to-front: the survivor with the highest list position goes to slot 0
                     const int rank = __popc(m >> lane) - 1;
                     const float X = a.x - rcx, Y = a.y - rcy;

@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(BF_THREADS) blend_fwd_kernel(const BlendFwdPar
     const int pix_x = wx0 + (lane & 7), pix_y = wy0 + (lane >> 3);
     const bool inside = pix_x < p.W && pix_y < p.H;
     const float pxf = (float)pix_x, pyf = (float)pix_y;
+    const float bx0 = (float)wx0, bx1 = (float)(wx0 + 7), by0 = (float)wy0, by1 = (float)(wy0 + 3);
 
     const uint2 range = p.ranges[tile];
     const int n = (int)(range.y - range.x);
@@ -95,8 +96,13 @@ __global__ void __launch_bounds__(BF_THREADS) blend_fwd_kernel(const BlendFwdPar
             const StageRec* st = sm.recs[s];
             for (int r0 = 0; r0 < cnt; r0 += 32) {
                 const int j = r0 + lane;
-                // cull mask written with the record (binning.cu: write_cull_masks): bit `warp` = may reach this warp's rectangle
-                const bool rel = (j < cnt) && ((__float_as_uint(st[j].pad.x) >> warp) & 1u);
+                bool rel = false;
+                if (j < cnt) {
+                    const float4 a = st[j].q0;
+                    const float4 c = st[j].q1;
+                    const float4 e = st[j].q3;
+                    rel = rect_may_contribute(a.x, a.y, c.x, c.y, c.z, a.z, e.z, e.w, bx0, bx1, by0, by1);
+                }
                 uint32_t m = __ballot_sync(0xffffffffu, rel);
                 while (m) {
                     const int k = __ffs(m) - 1;

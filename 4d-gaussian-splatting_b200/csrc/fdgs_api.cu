@@ -316,7 +316,7 @@ int fdgs_forward(const fdgs_forward_args* a, fdgs_alloc_fn geom_alloc, void* geo
         FDGS_STAGE(2, 1, fdgs::launch_bin_scatter(P, geom.binrec, grid_x, grid_y, img.bin_matrix, img.tile_offset, bin.keys, stream),
                    "bin_scatter");
         FDGS_STAGE(3, fdgs::tile_sort_pack_kernel_count(bin_info[1]),
-                   fdgs::launch_tile_sort_pack((int)img.tiles, grid_x, bin_info[1], num_rendered, img.ranges, bin.keys, geom.grec, bin.recs,
+                   fdgs::launch_tile_sort_pack((int)img.tiles, bin_info[1], num_rendered, img.ranges, bin.keys, geom.grec, bin.recs,
                                                bin.point_list, stream),
                    "tile_sort_pack");
     }

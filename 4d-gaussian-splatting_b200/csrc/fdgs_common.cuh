@@ -59,15 +59,17 @@ struct Camera {
 // kernels so that the activated values -- and with them radii, tiles, depth order -- do not change:
 //   exp      : expf (full-precision libdevice, what std::exp resolves to in ATen's exp kernel)
 //   sigmoid  : 1 / (1 + expf(-x))                                  (ATen sigmoid kernel, opmath = float)
-//   normalize: q / max(||q||_2, 1e-12); ATen reduces the 4 squares of a row with 4 cooperating lanes and a
-//              shuffle tree, i.e. (x^2 + y^2) + (z^2 + w^2)          (norm_kernel + block_x_reduce, dim 4)
+//   normalize: q / max(||q||_2, 1e-12); ATen's norm reduction of a 4-element row adds the rounded squares as
+//              (x^2 + z^2) + (y^2 + w^2) -- found by tools/probe_normalize.py on a B200 (all 24 x 2 plain-fp32
+//              orders tried against torch.linalg.vector_norm over 1M rows: only this pairing gives 0 differing words)
 __device__ __forceinline__ float act_exp(float x) { return expf(x); }
 __device__ __forceinline__ float act_sigmoid(float x) { return fdiv(1.0f, fadd(1.0f, expf(-x))); }
 __device__ __forceinline__ float quat_norm(const float4 q, int mode) {
     float s;
     if (mode == 1) s = fadd(fadd(fadd(fmul(q.x, q.x), fmul(q.y, q.y)), fmul(q.z, q.z)), fmul(q.w, q.w));   // sequential
     else if (mode == 2) s = ffma(q.w, q.w, ffma(q.z, q.z, ffma(q.y, q.y, fmul(q.x, q.x))));                 // fma chain
-    else s = fadd(fadd(fmul(q.x, q.x), fmul(q.y, q.y)), fadd(fmul(q.z, q.z), fmul(q.w, q.w)));              // pairwise tree
+    else if (mode == 3) s = fadd(fadd(fmul(q.x, q.x), fmul(q.y, q.y)), fadd(fmul(q.z, q.z), fmul(q.w, q.w)));   // (x,y)+(z,w)
+    else s = fadd(fadd(fmul(q.x, q.x), fmul(q.z, q.z)), fadd(fmul(q.y, q.y), fmul(q.w, q.w)));              // ATen: (x,z)+(y,w)
     return fsqrt(s);
 }
 __device__ __forceinline__ float4 act_normalize(const float4 q, int mode) {
@@ -287,13 +289,9 @@ static_assert(sizeof(InstRec) == 64, "InstRec must be 64 bytes");
 // 61 M of the ~110-190 M shared-memory wavefronts of each blend kernel); with an 80-byte stride 8 consecutive
 // records cover all 32 banks (20 j mod 32 = 0, 20, 8, 28, 16, 4, 24, 12) and the loads are conflict-free.  The
 // extra 16 bytes per instance are HBM traffic the blend kernels, at < 8 % of DRAM bandwidth, do not feel.
-// pad.x (as bits): CULL MASK -- bit w set = the instance may contribute to warp w's 8x4 pixel rectangle of its tile
-// (warps tile the 16x16 block 2 wide by 4 high; rect_may_contribute below), evaluated ONCE per instance when the
-// record is written (binning.cu: tile_sort_kernel) instead of once per warp and per blend pass.
 struct __align__(16) StageRec {
     float4 q0, q1, q2, q3, pad;
 };
-constexpr int kWarpRectW = 8, kWarpRectH = 4;   // pixel footprint of one warp of the blend kernels
 static_assert(sizeof(StageRec) == 80, "StageRec must be 80 bytes");
 constexpr uint32_t kStageRecBytes = 80u;
 

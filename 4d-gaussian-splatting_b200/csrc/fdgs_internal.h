@@ -84,7 +84,7 @@ cudaError_t launch_bin_scatter(int P, const uint4* binrec, int grid_x, int grid_
                                const uint32_t* tile_offset, uint64_t* keys, cudaStream_t stream);
 // sorts every tile's keys and writes the 64-byte instance records + the sorted index list
 int tile_sort_pack_kernel_count(int max_count);
-cudaError_t launch_tile_sort_pack(int num_tiles, int grid_x, int max_count, int R, const uint2* ranges, uint64_t* keys,
+cudaError_t launch_tile_sort_pack(int num_tiles, int max_count, int R, const uint2* ranges, uint64_t* keys,
                                   const InstRec* grec, StageRec* recs, uint32_t* point_list, cudaStream_t stream);
 cudaError_t launch_unpack_grec(int P, const InstRec* grec, const int* radii, float* depths, float* means2D,
                                float* conic_opacity, float* rgb, cudaStream_t stream);

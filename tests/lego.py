@@ -130,13 +130,50 @@ def make_optimizer(raw):
                              {"params": [raw["rot"], raw["rot_r"]], "lr": 1e-3}], eps=1e-15)
 
 
-def train_iteration(model, opt, cams, gts, it, batch, impl, device=DEV):
+_PYPREP = None
+
+
+def _pyprep():
+    """gaussian_renderer/pyprep.py by file path (importing the package would load the product's CUDA libraries)"""
+    global _PYPREP
+    if _PYPREP is None:
+        import importlib.util
+        import os
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "4d-gaussian-splatting_b200",
+                            "gaussian_renderer", "pyprep.py")
+        spec = importlib.util.spec_from_file_location("fdgs_pyprep_standalone_lego", path)
+        _PYPREP = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_PYPREP)
+    return _PYPREP
+
+
+def rigid_loss(model, impl, k=20):
+    """train.py:132-152 (configs/dnerf/lego.yaml:58 lambda_rigid = 1): neighbours of every centre among all centres,
+    weight exp(-100 d^2), penalise differences of the per-Gaussian velocity (mean offset over dt = 0.1).
+    ours: the uniform-grid search (fdgs.knn); reference arm: the brute-force scan pointops2's knnquery performs
+    (pointops2/src/knnquery/knnquery_cuda_kernel.cu:65-107 -- that extension cannot be built here, the same O(n^2)
+    algorithm runs through csrc/knn.cu's brute_force kernel)."""
+    from fdgs.knn import knn           # (with --rigid the reference arm maps libfdgs.so for the brute-force kNN kernel)
+    pyprep = _pyprep()
+    xyz = model.get_xyz
+    idx, dist = knn(xyz[None].contiguous().detach(), xyz[None].contiguous().detach(), k, brute_force=(impl != "ours"))
+    _, velocity = pyprep.conditional_covariance_and_offset(torch.cat([model.get_scaling, model.get_scaling_t], 1), 1.0,
+                                                           model.raw["rot"], model.raw["rot_r"], 0.1)
+    weight = torch.exp(-100 * dist)
+    vel_dist = torch.norm(velocity[idx] - velocity[None, :, None], p=2, dim=-1)
+    return (weight * vel_dist).sum() / k / xyz.shape[0]
+
+
+def train_iteration(model, opt, cams, gts, it, batch, impl, device=DEV, lambda_rigid=0.0):
     """One iteration of train.py's loop: `batch` sequential views, L1 loss / batch, one Adam step."""
     total = torch.zeros((), device=device)
     for b in range(batch):
         k = (it * batch + b) % len(cams)
         img = lego_render(model, cams[k], "ours" if impl == "ours" else "ref")
-        loss = (img - gts[k]).abs().mean() / batch
+        loss = (img - gts[k]).abs().mean()
+        if lambda_rigid > 0:
+            loss = loss + lambda_rigid * rigid_loss(model, impl)
+        loss = loss / batch
         loss.backward()
         total += loss.detach()
     opt.step()

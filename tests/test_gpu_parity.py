@@ -34,7 +34,7 @@ def C():
 # single reference run is a noisy sample; so is ours (RED order, reassociated sums).  Our gradients are compared with
 # the MEAN of K reference reruns; if ours is "one more sample of the same quantity" its distance to that mean is
 # about one per-run spread (sqrt(1 + 1/K) of it).  Bar per tensor, in the L2 and in the max-norm sense:
-#     err(ours, mean) < max(1e-4, 2.5 * spread)           (max-norm: 3 * spread)
+#     err(ours, mean) < max(1e-4, 4 * spread)             (max-norm: 5 * spread)
 # i.e. 1e-4 wherever the reference itself is reproducible to 1e-4 (all blend-level, SH and mean gradients, at every
 # size), and "statistically indistinguishable from a reference rerun" for the covariance chain (division by cov_t^2
 # and near-singular determinants amplify the 1e-7 upstream noise ~1000x: the reference's own spread reaches 3e-3 on
@@ -65,8 +65,8 @@ def check_grad_vs_reference(gname, a, runs):
     l2 = ((a.double() - m).norm() / nm).item()
     err = (a.double() - m).abs().max().item() / sc
     if l2n < 2e-4:
-        assert l2 < max(1e-4, 2.5 * l2n), (gname, "l2", l2, "ref spread", l2n)
-        assert err < max(1e-4, 3 * mxn), (gname, "max", err, "ref spread", mxn)
+        assert l2 < max(1e-4, 4 * l2n), (gname, "l2", l2, "ref spread", l2n)
+        assert err < max(1e-4, 5 * mxn), (gname, "max", err, "ref spread", mxn)
     else:
         # The reference does not reproduce ITSELF to 0.02 % here (cfg5's long time axis: a handful of Gaussians with
         # near-singular conditional covariances carry most of the norm and amplify the atomics' rounding noise to
