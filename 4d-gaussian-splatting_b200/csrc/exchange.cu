@@ -74,7 +74,28 @@ __global__ void __launch_bounds__(256) rows_zero_check_kernel(const CheckTable t
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
 
+// union bookkeeping of the exchange in one pass: given the inclusive scan `cs` of (radii > 0),
+// slot_of[i] = cs[i] - 1 for union Gaussians (else -1) and idx[slot] = i, the inverse map
+__global__ void __launch_bounds__(256) union_maps_kernel(long long P, const int* __restrict__ radii, const int* __restrict__ cs,
+                                                         int* __restrict__ slot_of, long long* __restrict__ idx) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    if (radii[i] > 0) {
+        const int sl = cs[i] - 1;
+        slot_of[i] = sl;
+        idx[sl] = i;
+    } else {
+        slot_of[i] = -1;
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_union_maps(long long P, const int* radii, const int* cs, int* slot_of, long long* idx, cudaStream_t stream) {
+    if (P <= 0) return cudaSuccess;
+    union_maps_kernel<<<(unsigned)((P + 255) / 256), 256, 0, stream>>>(P, radii, cs, slot_of, idx);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_rows_zero_check(int n, const float* const* tensors, const int* widths, long long P, const int* mask_radii,
                                    int* flag, cudaStream_t stream) {

@@ -436,8 +436,9 @@ int fdgs_sh_outer_sum(const fdgs_sh_sum_args* a, void* stream_v) {
     if (a->P <= 0) return FDGS_OK;
     if (a->V < 0 || a->K < 0 || a->M <= 0 || a->m0 <= 0 || a->m0 > a->M || a->D < 0 || a->D > 3 || a->D_t < 0 || a->D_t > 2)
         return fail(FDGS_ERR_INVALID_ARG, "bad V / K / M / m0 / degrees");
-    if (!a->slot_of || !a->means3D || !a->out0 || (a->m0 < a->M && !a->out1) || (a->V > 0 && a->K > 0 && !a->table))
-        return fail(FDGS_ERR_INVALID_ARG, "slot_of / means3D / table / outputs required");
+    if (!a->slot_of || !a->means3D || !a->out0 || (a->m0 < a->M && !a->out1) ||
+        (a->V > 0 && a->K > 0 && (!a->table || !a->union_idx || !a->dir_scratch)))
+        return fail(FDGS_ERR_INVALID_ARG, "slot_of / union_idx / dir_scratch / means3D / table / outputs required");
     if (a->rot_4d && (!a->scales || !a->scales_t || !a->rotations || !a->rotations_r || !a->ts))
         return fail(FDGS_ERR_INVALID_ARG, "rot_4d needs scales, scales_t, rotations, rotations_r, ts");
     const bool sh4d = !(a->gaussian_dim == 3 || a->force_sh_3d);
@@ -446,12 +447,22 @@ int fdgs_sh_outer_sum(const fdgs_sh_sum_args* a, void* stream_v) {
         return fail(FDGS_ERR_INVALID_ARG, "view block too small for K rows + metadata");
     fdgs::ShSumParams p;
     p.P = a->P; p.V = a->V; p.K = a->K; p.table = a->table; p.view_stride = a->view_stride; p.meta_off = a->meta_off;
-    p.slot_of = a->slot_of; p.means3D = a->means3D; p.ts = a->ts; p.scales = a->scales; p.scales_t = a->scales_t;
+    p.slot_of = a->slot_of; p.union_idx = a->union_idx; p.dirs = a->dir_scratch; p.means3D = a->means3D; p.ts = a->ts; p.scales = a->scales; p.scales_t = a->scales_t;
     p.rotations = a->rotations; p.rotations_r = a->rotations_r; p.scale_modifier = a->scale_modifier;
     p.time_duration = a->time_duration; p.rot_4d = a->rot_4d; p.gaussian_dim = a->gaussian_dim;
     p.force_sh_3d = a->force_sh_3d; p.D = a->D; p.D_t = a->D_t; p.M = a->M;
     p.out0 = a->out0; p.m0 = a->m0; p.out1 = (a->m0 < a->M) ? a->out1 : nullptr; p.accumulate = a->accumulate;
     FDGS_CUDA(fdgs::launch_sh_outer_sum(p, reinterpret_cast<cudaStream_t>(stream_v)), "sh_outer_sum");
+    g_kernel_launches += 1;
+    return FDGS_OK;
+}
+
+int fdgs_union_maps(long long P, const int* radii, const int* cs, int* slot_of, long long* idx, void* stream_v) {
+    g_last_error.clear();
+    if (P < 0) return fail(FDGS_ERR_INVALID_ARG, "bad P");
+    if (P == 0) return FDGS_OK;
+    if (!radii || !cs || !slot_of || !idx) return fail(FDGS_ERR_INVALID_ARG, "null argument");
+    FDGS_CUDA(fdgs::launch_union_maps(P, radii, cs, slot_of, idx, reinterpret_cast<cudaStream_t>(stream_v)), "union_maps");
     g_kernel_launches += 1;
     return FDGS_OK;
 }

@@ -184,6 +184,8 @@ struct ShSumParams {
     long long view_stride;    // floats per view block
     long long meta_off;       // offset of the view's metadata inside its block: timestamp, campos x, y, z
     const int* slot_of;       // [P] row of the Gaussian inside a view block, -1 = rendered by no view
+    const long long* union_idx;   // [K] the inverse map: Gaussian of every row (sorted)
+    float* dirs;              // [V][K][8] scratch: direction, temporal weights and colour factor per (view, row)
     const float* means3D;     // replicated Gaussian parameters, as handed to the rasterizer
     const float* ts;
     const float* scales;
@@ -202,6 +204,7 @@ cudaError_t launch_sh_outer_sum(const ShSumParams& p, cudaStream_t stream);
 cudaError_t launch_rows_zero_check(int n, const float* const* tensors, const int* widths, long long P, const int* mask_radii,
                                    int* flag, cudaStream_t stream);
 
+cudaError_t launch_union_maps(long long P, const int* radii, const int* cs, int* slot_of, long long* idx, cudaStream_t stream);
 cudaError_t launch_pack_rows(bool unpack, int n, float* const* tensors, const int* widths, const long long* block_off,
                              const long long* idx, long long K, float* flat, cudaStream_t stream);
 

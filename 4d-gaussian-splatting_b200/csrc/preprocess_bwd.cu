@@ -397,73 +397,96 @@ __global__ void __launch_bounds__(SB_THREADS, 6) sh_bwd_kernel(const PreprocessB
 // train.py:104-166): explicit round-to-nearest multiply then add, no fused rounding.
 // The direction is the one sh_ctx_init() sees: the time-shifted mean the forward wrote to out_means3D
 // (preprocess_fwd.cu: mean + dt * Sigma_xyz,t / Sigma_tt, same intrinsics, same order) minus the camera position.
-// 4 threads per Gaussian, thread kg owns the coefficients 4 kg .. 4 kg + 3 of each of the three 16-blocks.
-__global__ void __launch_bounds__(128) sh_outer_sum_kernel(const ShSumParams a) {
-    const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int idx = (int)(gt >> 2), kg = (int)(gt & 3);
-    if (idx >= a.P) return;
-    const int slot = a.slot_of[idx];
-    float acc[3][12];
-#pragma unroll
-    for (int b = 0; b < 3; ++b)
-#pragma unroll
-        for (int i = 0; i < 12; ++i) acc[b][i] = 0.f;
-
-    if (slot >= 0) {
+// Two kernels: directions / temporal weights per (union Gaussian, view), then the row sums (dense warps over the
+// union list) + zero rows for everything else.
+// Phase A: one thread per (union Gaussian k, view v): the view's unit direction to the (time-shifted) mean and its two
+// temporal weights, stored with the colour factor as dirs[(v K + k)] = { gx, gy, gz, tw1 | r, g, b, tw2 }.
+__global__ void __launch_bounds__(256) sh_outer_dir_kernel(const ShSumParams a) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)a.K * a.V) return;
+    const int k = (int)(t / a.V), v = (int)(t - (long long)k * a.V);
+    const long long idx = a.union_idx[k];
+    const float* blk = a.table + (size_t)v * a.view_stride;
+    const float r = blk[3 * (size_t)k + 0], g = blk[3 * (size_t)k + 1], b = blk[3 * (size_t)k + 2];
+    float4 o0 = make_float4(0.f, 0.f, 1.f, 0.f), o1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!(r == 0.f && g == 0.f && b == 0.f)) {   // rendered by view v
         const bool sh4d = !((a.gaussian_dim == 3) || a.force_sh_3d);
-        const int ncoef = (a.D + 1) * (a.D + 1);
-        const float ox = a.means3D[3 * idx + 0], oy = a.means3D[3 * idx + 1], oz = a.means3D[3 * idx + 2];
+        const float* meta = blk + a.meta_off;   // timestamp, camera position
+        const float timestamp = meta[0];
         const float t_g = (a.ts != nullptr) ? a.ts[idx] : 0.f;
-        float s03 = 0.f, s13 = 0.f, s23 = 0.f, cov_t = 1.f;
+        float mx = a.means3D[3 * idx + 0], my = a.means3D[3 * idx + 1], mz = a.means3D[3 * idx + 2];
         if (a.rot_4d) {
+            // the forward's mean shift (preprocess_fwd.cu), same intrinsics, same order
             const float mod = a.scale_modifier;
             Sigma4 S;
             build_M4(fmul(mod, a.scales[3 * idx + 0]), fmul(mod, a.scales[3 * idx + 1]), fmul(mod, a.scales[3 * idx + 2]),
                      fmul(mod, a.scales_t[idx]), reinterpret_cast<const float4*>(a.rotations)[idx],
                      reinterpret_cast<const float4*>(a.rotations_r)[idx], S.M);
             sigma_from_M(S);
-            s03 = S.s03; s13 = S.s13; s23 = S.s23; cov_t = S.s33;
+            const float dt = fsub(timestamp, t_g);
+            mx = ffma(dt, fdiv(S.s03, S.s33), mx);
+            my = ffma(dt, fdiv(S.s13, S.s33), my);
+            mz = ffma(dt, fdiv(S.s23, S.s33), mz);
         }
+        // exactly sh_ctx_init()
+        const float dx = mx - meta[1], dy = my - meta[2], dz = mz - meta[3];
+        const float len = sqrtf(dx * dx + dy * dy + dz * dz);
+        float tw1 = 0.f, tw2 = 0.f;
+        if (sh4d && a.D > 2 && a.D_t > 0) {
+            const float dir_t = t_g - timestamp;
+            tw1 = (float)cos(2 * FDGS_MY_PI * (double)dir_t / (double)a.time_duration);
+            if (a.D_t > 1) tw2 = (float)cos(2 * FDGS_MY_PI * (double)dir_t * 2 / (double)a.time_duration);
+        }
+        o0 = make_float4(dx / len, dy / len, dz / len, tw1);
+        o1 = make_float4(r, g, b, tw2);
+    }
+    float4* dst = reinterpret_cast<float4*>(a.dirs) + 2 * ((size_t)v * a.K + k);
+    dst[0] = o0;
+    dst[1] = o1;
+}
+
+// Phase B.  Blocks [0, union_blocks): 4 threads per UNION Gaussian (dense warps: the list a.union_idx), thread kg owns
+// the coefficients 4 kg .. 4 kg + 3 of each of the three 16-blocks, sums the V rank-one rows and stores the row.
+// Blocks beyond: the rows of all other Gaussians are zero-filled (4 threads per row, same store code).
+__global__ void __launch_bounds__(128) sh_outer_sum_kernel(const ShSumParams a, const int union_blocks) {
+    int idx, kg;
+    float acc[3][12];
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int i = 0; i < 12; ++i) acc[b][i] = 0.f;
+    if ((int)blockIdx.x >= union_blocks) {
+        const long long gt = (long long)(blockIdx.x - union_blocks) * blockDim.x + threadIdx.x;
+        idx = (int)(gt >> 2);
+        kg = (int)(gt & 3);
+        if (idx >= a.P || a.slot_of[idx] >= 0) return;
+    } else {
+        const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        const int k = (int)(gt >> 2);
+        kg = (int)(gt & 3);
+        if (k >= a.K) return;
+        idx = (int)a.union_idx[k];
+        const bool sh4d = !((a.gaussian_dim == 3) || a.force_sh_3d);
+        const int ncoef = (a.D + 1) * (a.D + 1);
+        const int nblk = (sh4d && a.D > 2 && a.D_t > 0) ? ((a.D_t > 1) ? 3 : 2) : 1;
         for (int v = 0; v < a.V; ++v) {
-            const float* blk = a.table + (size_t)v * a.view_stride;
-            const float r = blk[3 * (size_t)slot + 0], g = blk[3 * (size_t)slot + 1], b = blk[3 * (size_t)slot + 2];
-            if (r == 0.f && g == 0.f && b == 0.f) continue;   // not rendered by view v (or a zero colour gradient)
-            const float* meta = blk + a.meta_off;             // timestamp, camera position
-            const float timestamp = meta[0];
-            float mx = ox, my = oy, mz = oz;
-            if (a.rot_4d) {
-                const float dt = fsub(timestamp, t_g);
-                mx = ffma(dt, fdiv(s03, cov_t), mx);
-                my = ffma(dt, fdiv(s13, cov_t), my);
-                mz = ffma(dt, fdiv(s23, cov_t), mz);
-            }
-            // exactly sh_ctx_init()
-            const float dx = mx - meta[1], dy = my - meta[2], dz = mz - meta[3];
-            const float len = sqrtf(dx * dx + dy * dy + dz * dz);
-            float gx = dx / len, gy = dy / len, gz = dz / len;
-            float tw1 = 0.f, tw2 = 0.f;
-            int nblk = 1;
-            if (sh4d && a.D > 2 && a.D_t > 0) {
-                const float dir_t = t_g - timestamp;
-                tw1 = (float)cos(2 * FDGS_MY_PI * (double)dir_t / (double)a.time_duration);
-                nblk = 2;
-                if (a.D_t > 1) {
-                    tw2 = (float)cos(2 * FDGS_MY_PI * (double)dir_t * 2 / (double)a.time_duration);
-                    nblk = 3;
-                }
-            }
+            const float4* src = reinterpret_cast<const float4*>(a.dirs) + 2 * ((size_t)v * a.K + k);
+            const float4 d0 = src[0], d1 = src[1];
+            if (d1.x == 0.f && d1.y == 0.f && d1.z == 0.f) continue;   // not rendered by view v
+            float gx = d0.x, gy = d0.y, gz = d0.z;
+            const float tw1 = d0.w, tw2 = d1.w;
             ShDeriv S;
             sh_basis_deriv(gx, gy, gz, a.D, S);
-            const float drgb[3] = {r, g, b};
+            const float drgb[3] = {d1.x, d1.y, d1.z};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {   // select l[4 kg + j] without dynamic register indexing
                     if (q != kg) continue;
-                    const int k = 4 * q + j;
-                    if (k >= ncoef) continue;
-                    const float lk = S.l[k];
-                    const float w0 = (sh4d && k == 1) ? S.l[0] : lk;
+                    const int k2 = 4 * q + j;
+                    if (k2 >= ncoef) continue;
+                    const float lk = S.l[k2];
+                    const float w0 = (sh4d && k2 == 1) ? S.l[0] : lk;
 #pragma unroll
                     for (int ch = 0; ch < 3; ++ch) {
                         acc[0][3 * j + ch] = __fadd_rn(acc[0][3 * j + ch], __fmul_rn(w0, drgb[ch]));
@@ -860,8 +883,11 @@ cudaError_t launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t str
 
 cudaError_t launch_sh_outer_sum(const ShSumParams& p, cudaStream_t stream) {
     if (p.P <= 0) return cudaSuccess;
-    const long long threads = 4ll * p.P;
-    sh_outer_sum_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(p);
+    if ((long long)p.K * p.V > 0)
+        sh_outer_dir_kernel<<<(unsigned)(((long long)p.K * p.V + 255) / 256), 256, 0, stream>>>(p);
+    const int union_blocks = (int)((4ll * p.K + 127) / 128);
+    const int zero_blocks = (int)((4ll * p.P + 127) / 128);
+    sh_outer_sum_kernel<<<(unsigned)(union_blocks + zero_blocks), 128, 0, stream>>>(p, union_blocks);
     return cudaGetLastError();
 }
 

@@ -297,7 +297,8 @@ std::vector<torch::Tensor> RasterizeGaussiansBackwardRaw(FDGS_BWD_PARAMS, const 
 
 // rebuild + sum the dL_dsh rows of all views from the gathered colour factors (include/fdgs.h: fdgs_sh_outer_sum)
 void ShOuterSum(const torch::Tensor& table, const int64_t view_stride, const int64_t meta_off, const int64_t V,
-                const int64_t K, const torch::Tensor& slot_of, const torch::Tensor& means3D, const torch::Tensor& ts,
+                const int64_t K, const torch::Tensor& slot_of, const torch::Tensor& union_idx, const torch::Tensor& means3D,
+                const torch::Tensor& ts,
                 const torch::Tensor& scales, const torch::Tensor& scales_t, const torch::Tensor& rotations,
                 const torch::Tensor& rotations_r, const double scale_modifier, const double time_duration,
                 const bool rot_4d, const int64_t gaussian_dim, const bool force_sh_3d, const int64_t D, const int64_t D_t,
@@ -315,6 +316,11 @@ void ShOuterSum(const torch::Tensor& table, const int64_t view_stride, const int
     fdgs_sh_sum_args a;
     memset(&a, 0, sizeof(a));
     a.P = P; a.V = (int)V; a.K = (int)K; a.table = fptr(tb_c); a.view_stride = view_stride; a.meta_off = meta_off;
+    TORCH_CHECK(union_idx.is_cuda() && union_idx.scalar_type() == torch::kInt64 && union_idx.is_contiguous() &&
+                union_idx.numel() == K, "fdgs: union_idx must be int64 CUDA [K]");
+    torch::Tensor dirs = torch::empty({std::max<int64_t>(V * K * 8, 1)}, means3D.options().dtype(torch::kFloat32));
+    a.union_idx = reinterpret_cast<const long long*>(union_idx.data_ptr<int64_t>());
+    a.dir_scratch = dirs.data_ptr<float>();
     a.slot_of = slot_of.data_ptr<int>(); a.means3D = fptr(m_c); a.ts = fptr(ts_c); a.scales = fptr(sc_c);
     a.scales_t = fptr(sct_c); a.rotations = fptr(rot_c); a.rotations_r = fptr(rotr_c);
     a.scale_modifier = (float)scale_modifier; a.time_duration = (float)time_duration; a.rot_4d = rot_4d;
@@ -326,6 +332,21 @@ void ShOuterSum(const torch::Tensor& table, const int64_t view_stride, const int
     a.accumulate = accumulate;
     if (V > 0) TORCH_CHECK(tb_c.numel() >= V * view_stride, "fdgs: factor table too small");
     check(fdgs_sh_outer_sum(&a, (void*)stream), "sh_outer_sum");
+}
+
+// (slot_of int32 [P], idx int64 [K]) from the radii, their inclusive prefix sum cs and K = cs[-1] (known to the host)
+std::tuple<torch::Tensor, torch::Tensor> UnionMaps(const torch::Tensor& radii, const torch::Tensor& cs, const int64_t K) {
+    TORCH_CHECK(radii.is_cuda() && radii.scalar_type() == torch::kInt32 && radii.is_contiguous() && cs.is_cuda() &&
+                cs.scalar_type() == torch::kInt32 && cs.is_contiguous() && cs.numel() == radii.numel(),
+                "fdgs: radii / cs must be contiguous int32 CUDA tensors of equal length");
+    const c10::cuda::CUDAGuard guard(radii.device());
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream().stream();
+    torch::Tensor slot_of = torch::empty_like(radii);
+    torch::Tensor idx = torch::empty({K}, radii.options().dtype(torch::kInt64));
+    check(fdgs_union_maps(radii.numel(), radii.data_ptr<int>(), cs.data_ptr<int>(), slot_of.data_ptr<int>(),
+                          reinterpret_cast<long long*>(idx.data_ptr<int64_t>()), (void*)stream),
+          "union_maps");
+    return std::make_tuple(slot_of, idx);
 }
 
 // 1-element int32 tensor, non-zero if a row of `tensors` outside radii > 0 is not all-zero (sparse-exchange guard)
@@ -567,6 +588,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("rasterize_gaussians_backward_raw", &RasterizeGaussiansBackwardRaw);
     m.def("sh_outer_sum", &ShOuterSum);
     m.def("check_rows_zero", &CheckRowsZero);
+    m.def("union_maps", &UnionMaps);
     m.def("mark_visible", &markVisible);
     m.def("debug_export_geom", &DebugExportGeom);
     m.def("debug_export_binning", &DebugExportBinning);

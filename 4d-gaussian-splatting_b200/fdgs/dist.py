@@ -256,9 +256,19 @@ class ViewParallelStep:
         if world > 1:
             dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=group)
         mask = union > 0
-        idx = torch.nonzero(mask).squeeze(1)                            # host sync: K sizes the buffers
-        K = int(idx.numel())
-        sparse_ok = int(bad.item()) == 0 and K <= self.dense_above * P
+        if union.is_cuda:
+            # one scan + one pass (csrc/exchange.cu: union_maps_kernel); K and the guard flag in ONE host read
+            cs = torch.cumsum(mask, 0, dtype=torch.int32)
+            k_bad = torch.stack([cs[-1] if P > 0 else cs.new_zeros(()), bad[0]]).tolist()   # host sync: K sizes the buffers
+            K, bad_flag = int(k_bad[0]), int(k_bad[1])
+            import fdgs
+            slot_of, idx = fdgs.ext().union_maps(union.contiguous(), cs, K)
+        else:
+            idx = torch.nonzero(mask).squeeze(1)
+            K, bad_flag = int(idx.numel()), int(bad.item())
+            slot_of = torch.where(mask, torch.cumsum(mask.to(torch.int32), 0, dtype=torch.int32) - 1,
+                                  torch.full_like(union, -1)).to(torch.int32).contiguous()
+        sparse_ok = bad_flag == 0 and K <= self.dense_above * P
         self._mark("union_index_build")
         self.info = {"K": K, "union_fraction": K / max(P, 1), "geometry_path": "rows" if sparse_ok else "dense",
                      "views_local": len(self.views)}
@@ -305,14 +315,12 @@ class ViewParallelStep:
                 self._mark("factor_allgather")
             else:
                 table = local
-            slot_of = torch.where(mask, torch.cumsum(mask.to(torch.int32), 0, dtype=torch.int32) - 1,
-                                  torch.full_like(union, -1)).to(torch.int32).contiguous()
             outs = []
             for p in sh_params:
                 if p.grad is None:
                     p.grad = torch.empty_like(p)
                 outs.append(p.grad)
-            self._outer_sum(table, stride, meta_off, table.shape[0], K, slot_of, outs)
+            self._outer_sum(table, stride, meta_off, table.shape[0], K, slot_of, outs, idx)
             self._mark("sh_outer_sum")
             self.info.update(views_total=int(table.shape[0]), factor_bytes_per_rank=int(local.numel() * 4))
         self.views = []
@@ -321,7 +329,7 @@ class ViewParallelStep:
             self.info["phase_ms"] = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(self._marks[:-1], self._marks[1:])}
         return st
 
-    def _outer_sum(self, table, stride, meta_off, V, K, slot_of, outs):
+    def _outer_sum(self, table, stride, meta_off, V, K, slot_of, outs, idx):
         # the replicated inputs and the per-step constants come from any recorded view; a rank without views (more
         # ranks than views) has none and must be handed them by the caller through `outer_sum_fn`
         if self._outer_sum_fn is not None:
@@ -337,7 +345,7 @@ class ViewParallelStep:
                      rotations=act(i["rotations"], torch.nn.functional.normalize),
                      rotations_r=act(i["rotations_r"], torch.nn.functional.normalize))
         import fdgs
-        fdgs.ext().sh_outer_sum(table, stride, meta_off, V, K, slot_of, i["means3D"], i["ts"], i["scales"], i["scales_t"],
+        fdgs.ext().sh_outer_sum(table, stride, meta_off, V, K, slot_of, idx, i["means3D"], i["ts"], i["scales"], i["scales_t"],
                                 i["rotations"], i["rotations_r"], float(s.scale_modifier), float(s.time_duration),
                                 bool(s.rot_4d), int(s.gaussian_dim), bool(s.force_sh_3d), int(s.sh_degree),
                                 int(s.sh_degree_t), outs, False)

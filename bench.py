@@ -75,13 +75,19 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu = gpu_index
+        # nvidia-smi numbers the physical GPUs, CUDA numbers the visible ones: select by UUID when torch exposes it
+        self.gpu = str(gpu_index)
+        try:
+            u = str(torch.cuda.get_device_properties(gpu_index).uuid)
+            self.gpu = u if u.startswith("GPU-") else "GPU-" + u
+        except Exception:
+            pass
         self.proc = None
         self.lines = []
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.gpu, "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
@@ -112,7 +118,8 @@ class ClockSampler:
                     reasons.add(name)
         busy = [s for s in sm if s > 300] or sm
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "gpu": self.gpu,
+                "sm_mhz_min": min(busy) if busy else None}
 
 
 def measured_peak():
@@ -800,6 +807,10 @@ def main():
                 cpu_baseline["cfg1"] = cpu_cfg1_baseline()
                 py_pre = python_preprocess_baseline(wl)
 
+    if eff_world > 1 and args.impl == "ours":
+        sys.stderr.write("[bench] rank %d on %s (%s): ms/step %.3f, stage_ms %s, clocks %s\n" % (
+            rank, device, os.environ.get("CUDA_VISIBLE_DEVICES", "all visible"), ms_step,
+            {k: round(v, 3) for k, v in (stage_ms or {}).items()}, clocks))
     if rank == 0:
         line = {
             "metric": spec["metric"],

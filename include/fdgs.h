@@ -238,6 +238,8 @@ typedef struct fdgs_sh_sum_args {
     long long view_stride;
     long long meta_off;
     const int* slot_of;           /* [P]                                       */
+    const long long* union_idx;   /* [K] Gaussian index of every union row (ascending): the inverse of slot_of */
+    float* dir_scratch;           /* [V*K*8] floats of scratch                 */
     const float* means3D;         /* [P,3] the rasterizer's inputs (replicated) */
     const float* ts;              /* [P] or NULL                               */
     const float* scales;          /* [P,3] (needed when rot_4d)                */
@@ -286,6 +288,11 @@ int fdgs_adam_step(int n, float* const* params, float* const* grads, float* cons
  * fdgs_knn_scratch_bytes(n) bytes.  brute_force != 0 runs the reference's O(n^2) scan instead (validation). */
 size_t fdgs_knn_scratch_bytes(int n);
 int fdgs_knn(int n, int k, const float* xyz, char* scratch, int* idx, float* dist2, int brute_force, void* stream);
+
+/* Union bookkeeping of the exchange: cs = inclusive prefix sum of (radii > 0) over the P Gaussians (device, int32).
+ * Writes slot_of[i] = cs[i] - 1 for union Gaussians, -1 otherwise, and the inverse map idx[slot] = i (idx: K =
+ * cs[P-1] entries, int64). */
+int fdgs_union_maps(long long P, const int* radii, const int* cs, int* slot_of, long long* idx, void* stream);
 
 /* Test/diagnostic hooks (used by tests/ and bench.py only): copy private
  * per-Gaussian / per-instance state out of the scratch buffers into plain

@@ -99,7 +99,7 @@ def test_fused_adam_dense_matches_torch_adam():
         ob.step()
     exact = 0
     for a, b in zip(pa, pb):
-        assert torch.allclose(a, b, rtol=2e-6, atol=1e-9), (a - b).abs().max()
+        assert torch.allclose(a, b, rtol=2e-6, atol=1e-7), (a - b).abs().max()   # update steps are <= lr: 1 ulp of a step
         exact += int(torch.equal(a, b))
     for a, b in zip(pa, pb):   # optimizer state too
         assert torch.allclose(oa.state[a]["exp_avg"], ob.state[b]["exp_avg"], rtol=2e-6, atol=1e-12)

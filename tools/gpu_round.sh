@@ -16,7 +16,7 @@ if has golden; then
   grep -E "golden written|diff=|CONFIG" $OUT/${TAG}_golden.log | tail -40
 fi
 if has tests; then
-  timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1
+  timeout 1500 python -m pytest tests -m gpu -q > $OUT/${TAG}_pytest.log 2>&1
   echo "pytest exit $?" >> $OUT/${TAG}_pytest.log
   tail -15 $OUT/${TAG}_pytest.log
 fi
