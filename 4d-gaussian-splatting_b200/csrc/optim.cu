@@ -10,9 +10,9 @@
 //           rows of all others are exactly zero).  Rows not listed keep parameters AND moments untouched: this is the
 //           "sparse Adam" of later 3DGS code bases, not torch's dense semantics (a dense step also moves unrendered
 //           Gaussians along their decaying momentum); it is opt-in.
-// Arithmetic follows torch's single-tensor Adam, op for op in fp32:
-//   m = m + (g - m) * (1 - b1)          (Tensor.lerp_)
-//   v = v * b2 + (1 - b2) * g * g       (mul_ + addcmul_)
+// Arithmetic follows torch's multi-tensor (foreach) Adam -- the default on CUDA -- op for op in fp32:
+//   m = m + (g - m) * (1 - b1)          (_foreach_lerp_)
+//   v = v * b2 + (g * g) * (1 - b2)     (_foreach_mul_ + _foreach_addcmul_: the product of the tensors first)
 //   p = p - (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)
 // with bc1 = 1 - b1^t, bc2 = 1 - b2^t computed on the host in double like torch does.
 #include "../../include/fdgs.h"
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamTable tb, long long
         const float g = G[e];
         float m = M[e], v = V[e];
         m = __fmaf_rn(__fsub_rn(g, m), w1, m);                          // lerp_: m + w1 * (g - m)
-        v = __fmaf_rn(__fmul_rn(w2, g), g, __fmul_rn(v, beta2));        // addcmul_: v*b2 + (w2*g)*g
+        v = __fmaf_rn(__fmul_rn(g, g), w2, __fmul_rn(v, beta2));        // _foreach_mul_ + _foreach_addcmul_: v*b2 + (g*g)*w2
         const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), sqrt_bc2), eps);     // sqrt(v) / sqrt(bc2) + eps
         P[e] = __fmaf_rn(-ss, __fdiv_rn(m, denom), P[e]);               // addcdiv_: p + (-step_size) * (m / denom)
         M[e] = m;

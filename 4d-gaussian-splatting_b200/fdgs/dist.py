@@ -42,6 +42,16 @@ def shard_views(num_views: int, rank: int, world: int) -> List[int]:
     return list(range(start, start + base + (1 if rank < rem else 0)))
 
 
+_SIDE_STREAMS: Dict[str, "torch.cuda.Stream"] = {}
+
+
+def _side_stream(device):
+    key = str(device)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 def _world(group=None) -> int:
     return dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
 
@@ -192,7 +202,11 @@ class ViewParallelStep:
     _active: Optional["ViewParallelStep"] = None
 
     def __init__(self, P: int, device, group=None, sh_factors: bool = True, dense_above: float = 0.6,
-                 outer_sum_fn: Optional[Callable] = None):
+                 outer_sum_fn: Optional[Callable] = None, expected_views: Optional[int] = None):
+        """expected_views: how many views THIS rank renders in the step.  When given (and on CUDA), the union of the
+        rendered Gaussians is built as soon as the last local FORWARD has run -- MAX all-reduce of the radii, prefix
+        sum and its total to pinned host memory on a side stream -- so that this collective, the scan and the host's
+        wait for the row count K all hide behind the backward pass instead of following it."""
         self.P, self.device, self.group = P, device, group
         self.sh_factors = sh_factors
         self.dense_above = dense_above
@@ -202,6 +216,10 @@ class ViewParallelStep:
         self.info: Dict[str, object] = {}
         self.profile = False            # True: CUDA events around the phases of finish() -> info["phase_ms"] (one sync)
         self._marks = []
+        self.expected_views = expected_views
+        self._fwd_radii = None
+        self._fwd_count = 0
+        self._early = None              # (radii_max, prefix_sum, event, pinned K) once the early union was launched
 
     def _mark(self, name):
         if self.profile and torch.cuda.is_available() and str(self.device).startswith("cuda"):
@@ -230,6 +248,30 @@ class ViewParallelStep:
     def record_view(self, factors, settings, inputs):
         self.views.append(_ViewRecord(factors, settings, inputs))
 
+    def on_forward(self, radii: torch.Tensor):
+        """Called by the rasterizer's forward (autograd hook): accumulate MAX radii; after the last expected view start
+        the union build on a side stream (see __init__)."""
+        if self.expected_views is None or not radii.is_cuda:
+            return
+        r = radii.to(torch.int32)
+        self._fwd_radii = r.clone() if self._fwd_radii is None else torch.max(self._fwd_radii, r)
+        self._fwd_count += 1
+        if self._fwd_count == self.expected_views:
+            cur = torch.cuda.current_stream()
+            side = _side_stream(radii.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                rmax = self._fwd_radii
+                rmax.record_stream(side)
+                if _world(self.group) > 1:
+                    dist.all_reduce(rmax, op=dist.ReduceOp.MAX, group=self.group)
+                cs = torch.cumsum(rmax > 0, 0, dtype=torch.int32)
+                k_host = torch.empty(1, dtype=torch.int32).pin_memory()
+                k_host.copy_(cs[-1:] if self.P > 0 else cs.new_zeros(1), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            self._early = (rmax, cs, ev, k_host)
+
     def add_view_stats(self, viewspace_grad: torch.Tensor, radii: torch.Tensor):
         self.stats.add_view(viewspace_grad, radii)
 
@@ -240,38 +282,47 @@ class ViewParallelStep:
         st = self.stats
         self._marks = []
         self._mark("start")
-        st.reduce_radii(group)                                          # union of rendered Gaussians + MAX statistic
-        self._mark("radii_max_allreduce")
         grads = []
         for p in geometry_params:
             if p.grad is None:
                 p.grad = torch.zeros_like(p)
             grads.append(p.grad)
         have_factors = len(self.views) > 0
+        cs = None
+        if self._early is not None:
+            # the union was built behind the backward pass: wait for ITS event only (not for the whole stream)
+            rmax, cs, ev, k_host = self._early
+            ev.synchronize()
+            torch.cuda.current_stream().wait_event(ev)
+            st.max_radii, st.radii_reduced = rmax, True
+            K = int(k_host[0])
+        else:
+            st.reduce_radii(group)                                      # union of rendered Gaussians + MAX statistic
+        self._mark("radii_max_allreduce")
         if world == 1 and not have_factors:
             return st
 
         union = st.max_radii
+        # guard of the sparse exchange (rows outside the union must be zero): checked on the device, MAX-reduced, read
+        # at the END of finish() -- the optimistic sparse path is repaired there in the (rare) case it was wrong
         bad = _rows_zero_outside(grads, union) if (grads and world > 1) else torch.zeros(1, dtype=torch.int32, device=union.device)
-        if world > 1:
-            dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=group)
+        bad_work = dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=group, async_op=True) if world > 1 else None
         mask = union > 0
         if union.is_cuda:
-            # one scan + one pass (csrc/exchange.cu: union_maps_kernel); K and the guard flag in ONE host read
-            cs = torch.cumsum(mask, 0, dtype=torch.int32)
-            k_bad = torch.stack([cs[-1] if P > 0 else cs.new_zeros(()), bad[0]]).tolist()   # host sync: K sizes the buffers
-            K, bad_flag = int(k_bad[0]), int(k_bad[1])
             import fdgs
-            slot_of, idx = fdgs.ext().union_maps(union.contiguous(), cs, K)
+            if cs is None:
+                cs = torch.cumsum(mask, 0, dtype=torch.int32)
+                K = int(cs[-1].item()) if P > 0 else 0                  # host sync: K sizes the buffers
+            slot_of, idx = fdgs.ext().union_maps(union.contiguous(), cs, K)   # one pass (csrc/exchange.cu)
         else:
             idx = torch.nonzero(mask).squeeze(1)
-            K, bad_flag = int(idx.numel()), int(bad.item())
+            K = int(idx.numel())
             slot_of = torch.where(mask, torch.cumsum(mask.to(torch.int32), 0, dtype=torch.int32) - 1,
                                   torch.full_like(union, -1)).to(torch.int32).contiguous()
-        sparse_ok = bad_flag == 0 and K <= self.dense_above * P
+        sparse_ok = K <= self.dense_above * P
         self._mark("union_index_build")
         self.info = {"K": K, "union_fraction": K / max(P, 1), "geometry_path": "rows" if sparse_ok else "dense",
-                     "views_local": len(self.views)}
+                     "views_local": len(self.views), "early_union": self._early is not None}
 
         # -- geometry bucket + the two SUM statistics: one flat buffer, one collective
         if world > 1:
@@ -324,6 +375,20 @@ class ViewParallelStep:
             self._mark("sh_outer_sum")
             self.info.update(views_total=int(table.shape[0]), factor_bytes_per_rank=int(local.numel() * 4))
         self.views = []
+        self._early, self._fwd_radii, self._fwd_count = None, None, 0
+        if world > 1:
+            bad_work.wait()
+            if int(bad.item()) != 0 and sparse_ok:
+                # some rank holds gradients outside the union (a loss over ALL Gaussians): the union's rows are summed
+                # already, sum the remaining rows densely
+                self.info["geometry_path"] = "rows + dense repair"
+                outside = (~mask)
+                for g in grads + [st.grad_norm_sum, st.visibility_count]:
+                    m = outside.view(-1, *([1] * (g.dim() - 1)))
+                    tmp = g * m
+                    dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
+                    g.mul_(~m).add_(tmp)
+            self._mark("guard_check")
         if self._marks:
             torch.cuda.synchronize()
             self.info["phase_ms"] = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(self._marks[:-1], self._marks[1:])}

@@ -45,6 +45,15 @@ def _invoke(fn, args, debug, dump_name):
         raise
 
 
+def _notify_forward(radii):
+    """View-parallel step (fdgs/dist.py): the radii of a view are known after its forward -- lets the step build the
+    union of rendered Gaussians behind the backward pass."""
+    from fdgs.dist import ViewParallelStep
+    step = ViewParallelStep.current()
+    if step is not None:
+        step.on_forward(radii)
+
+
 class GaussianRasterizationSettings(NamedTuple):
     """Per-view constants (reference: :227-245; names and order are the contract)."""
     image_height: int
@@ -83,6 +92,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         (num_rendered, color, flow, depth, T, radii, geom_buf, binning_buf, img_buf, covs_com,
          out_means3D) = _invoke(_C.rasterize_gaussians, args, s.debug, "snapshot_fw.dump")
 
+        _notify_forward(radii)
         ctx.raster_settings = s
         ctx.num_rendered = num_rendered
         ctx.prefilter_var = prefilter_var
@@ -160,6 +170,7 @@ class _RasterizeGaussiansRaw(torch.autograd.Function):
                 s.time_duration, s.rot_4d, s.gaussian_dim, s.force_sh_3d, s.prefiltered, s.debug, sh_rest, True)
         (num_rendered, color, flow, depth, T, radii, geom_buf, binning_buf, img_buf, covs_com,
          out_means3D) = _invoke(_C.rasterize_gaussians_raw, args, s.debug, "snapshot_fw.dump")
+        _notify_forward(radii)
         ctx.raster_settings = s
         ctx.num_rendered = num_rendered
         ctx.prefilter_var = prefilter_var

@@ -256,7 +256,7 @@ class Runner:
         step = None
         if self.exchange:
             from fdgs.dist import ViewParallelStep
-            step = ViewParallelStep(wl.P, wl.device)
+            step = ViewParallelStep(wl.P, wl.device, expected_views=len(wl.view_ids))
             step.profile = self.profile_exchange
             step.__enter__()
         result = None

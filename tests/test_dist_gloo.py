@@ -248,3 +248,35 @@ def test_sparse_exchange_detects_non_rasterizer_gradients():
     out = mgr.dict()
     mp.spawn(_dense_guard_worker, args=(world, _free_port(), P, out), nprocs=world, join=True)
     assert all(out[r] for r in range(world))
+
+
+def _repair_worker(rank, world, port, P, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(40 + rank)
+        vis = torch.rand(P, generator=g) < 0.25
+        radii = vis.to(torch.int32) * 7
+        xyz = torch.zeros(P, 3, requires_grad=True)
+        xyz.grad = torch.randn(P, 3, generator=g)            # NOT confined to the rendered rows (e.g. a rigidity loss)
+        want = xyz.grad.clone()
+        dist.all_reduce(want)
+        step = fdist.ViewParallelStep(P, "cpu", sh_factors=False)
+        step.add_view_stats(torch.randn(P, 3, generator=g) * vis[:, None], radii)
+        step.finish([xyz], [])
+        out[rank] = (torch.allclose(xyz.grad, want, rtol=1e-6, atol=1e-6), step.info["geometry_path"])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_view_parallel_step_repairs_non_rasterizer_gradients():
+    """the optimistic sparse exchange of ViewParallelStep.finish(): when the device-side guard (read at the end) says
+    some rank had gradient rows outside the union, the remaining rows are summed densely -- the result is the dense sum"""
+    world, P = 2, 400
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_repair_worker, args=(world, _free_port(), P, out), nprocs=world, join=True)
+    for r in range(world):
+        ok, path = out[r]
+        assert ok and path == "rows + dense repair"

@@ -98,8 +98,12 @@ def test_fused_adam_dense_matches_torch_adam():
         oa.step()
         ob.step()
     exact = 0
-    for a, b in zip(pa, pb):
-        assert torch.allclose(a, b, rtol=2e-6, atol=1e-7), (a - b).abs().max()   # update steps are <= lr: 1 ulp of a step
+    for a, b, lr in zip(pa, pb, lrs):
+        # every step moves a parameter by <= lr; the two implementations may differ by an ulp of the moments per step
+        d = (a - b).abs()
+        i = int(d.argmax())
+        assert float(d.max()) <= 1e-5 * lr * K + 2e-7 * float(a.abs().max()), (
+            "lr", lr, "max diff", float(d.max()), "at", i, float(a.flatten()[i]), float(b.flatten()[i]))
         exact += int(torch.equal(a, b))
     for a, b in zip(pa, pb):   # optimizer state too
         assert torch.allclose(oa.state[a]["exp_avg"], ob.state[b]["exp_avg"], rtol=2e-6, atol=1e-12)
