@@ -106,8 +106,8 @@ def test_fused_adam_dense_matches_torch_adam():
             "lr", lr, "max diff", float(d.max()), "at", i, float(a.flatten()[i]), float(b.flatten()[i]))
         exact += int(torch.equal(a, b))
     for a, b in zip(pa, pb):   # optimizer state too
-        assert torch.allclose(oa.state[a]["exp_avg"], ob.state[b]["exp_avg"], rtol=2e-6, atol=1e-12)
-        assert torch.allclose(oa.state[a]["exp_avg_sq"], ob.state[b]["exp_avg_sq"], rtol=2e-6, atol=1e-15)
+        assert torch.allclose(oa.state[a]["exp_avg"], ob.state[b]["exp_avg"], rtol=2e-6, atol=2e-7)      # |g| ~ 1: an ulp of g
+        assert torch.allclose(oa.state[a]["exp_avg_sq"], ob.state[b]["exp_avg_sq"], rtol=2e-6, atol=1e-9)
     print("fused Adam: %d of %d tensors bit-identical to torch.optim.Adam after %d steps" % (exact, len(pa), K))
 
 
