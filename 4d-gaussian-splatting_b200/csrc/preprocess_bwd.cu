@@ -445,27 +445,58 @@ __global__ void __launch_bounds__(256) sh_outer_dir_kernel(const ShSumParams a) 
     dst[1] = o1;
 }
 
+// Coalesced store of one gradient row (row_floats = 3 M values; `src` = its first min(row_floats, 144) values in shared
+// memory or NULL for a zero row) by the 32 lanes of a warp.  One tensor [P,M,3] with 16-byte rows: float4 stores, 512
+// contiguous bytes per instruction; split tensors (features_dc [P,1,3] | features_rest [P,M-1,3]): 4-byte stores.
+__device__ __forceinline__ void store_sh_row(const ShSumParams& a, size_t idx, const float* src, int lane) {
+    const int row_floats = 3 * a.M;
+    if (a.out1 == nullptr && (a.M % 4) == 0 && !a.accumulate) {
+        float4* row = reinterpret_cast<float4*>(a.out0 + idx * row_floats);
+        const int nq = row_floats / 4;
+        for (int q = lane; q < nq; q += 32) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (src != nullptr && q < 36) v = *reinterpret_cast<const float4*>(src + 4 * q);
+            row[q] = v;
+        }
+    } else {
+        const int m0 = a.m0;
+        for (int f = lane; f < row_floats; f += 32) {
+            const float v = (src != nullptr && f < 144) ? src[f] : 0.f;
+            const int c = f / 3, ch = f - 3 * c;
+            float* dst = (c < m0) ? a.out0 + (idx * m0 + c) * 3 + ch : a.out1 + (idx * (a.M - m0) + (c - m0)) * 3 + ch;
+            *dst = a.accumulate ? *dst + v : v;
+        }
+    }
+}
+
 // Phase B.  Blocks [0, union_blocks): 4 threads per UNION Gaussian (dense warps: the list a.union_idx), thread kg owns
-// the coefficients 4 kg .. 4 kg + 3 of each of the three 16-blocks, sums the V rank-one rows and stores the row.
-// Blocks beyond: the rows of all other Gaussians are zero-filled (4 threads per row, same store code).
+// the coefficients 4 kg .. 4 kg + 3 of each of the three 16-blocks and sums the V rank-one rows into registers; the 32
+// rows of a block are staged in shared memory and stored warp-per-row, fully coalesced.
+// Blocks beyond: the rows of all other Gaussians are zero-filled, warp per row.
+constexpr int SO_ROWS = 32;          // union Gaussians per block (128 threads)
+constexpr int SO_STRIDE = 148;       // floats per staged row (144 + padding: conflict-free float4 stores)
 __global__ void __launch_bounds__(128) sh_outer_sum_kernel(const ShSumParams a, const int union_blocks) {
-    int idx, kg;
+    __shared__ __align__(16) float rowbuf[SO_ROWS][SO_STRIDE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if ((int)blockIdx.x >= union_blocks) {
+        // zero rows: this block covers 128 consecutive Gaussians, a warp per row
+        const long long base = (long long)(blockIdx.x - union_blocks) * 128;
+        for (int r = warp; r < 128; r += 4) {
+            const long long idx = base + r;
+            if (idx >= a.P) break;
+            if (a.slot_of[idx] >= 0 || a.accumulate) continue;
+            store_sh_row(a, (size_t)idx, nullptr, lane);
+        }
+        return;
+    }
+    const int k = blockIdx.x * SO_ROWS + (threadIdx.x >> 2);
+    const int kg = threadIdx.x & 3;
     float acc[3][12];
 #pragma unroll
     for (int b = 0; b < 3; ++b)
 #pragma unroll
         for (int i = 0; i < 12; ++i) acc[b][i] = 0.f;
-    if ((int)blockIdx.x >= union_blocks) {
-        const long long gt = (long long)(blockIdx.x - union_blocks) * blockDim.x + threadIdx.x;
-        idx = (int)(gt >> 2);
-        kg = (int)(gt & 3);
-        if (idx >= a.P || a.slot_of[idx] >= 0) return;
-    } else {
-        const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-        const int k = (int)(gt >> 2);
-        kg = (int)(gt & 3);
-        if (k >= a.K) return;
-        idx = (int)a.union_idx[k];
+    if (k < a.K) {
         const bool sh4d = !((a.gaussian_dim == 3) || a.force_sh_3d);
         const int ncoef = (a.D + 1) * (a.D + 1);
         const int nblk = (sh4d && a.D > 2 && a.D_t > 0) ? ((a.D_t > 1) ? 3 : 2) : 1;
@@ -497,40 +528,22 @@ __global__ void __launch_bounds__(128) sh_outer_sum_kernel(const ShSumParams a, 
             }
         }
     }
-
-    // ---- store: coefficients 16 b + 4 kg + j of row idx; the row may be split over two tensors (features_dc |
-    // features_rest of the reference's GaussianModel, scene/gaussian_model.py:210-214) ------------------------------
-    const int M = a.M, m0 = a.m0;
-    if (a.out1 == nullptr && (M % 4) == 0 && !a.accumulate) {
-        float4* row = reinterpret_cast<float4*>(a.out0 + (size_t)idx * 3 * M);
+    // stage: coefficients 16 b + 4 kg + j of the row -> floats 48 b + 12 kg + 3 j + ch
+    {
+        float* dst = &rowbuf[threadIdx.x >> 2][0];
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
-            if (16 * b + 4 * kg + 3 < M) {
-                float4* dst = row + (48 * b + 12 * kg) / 4;
-                dst[0] = make_float4(acc[b][0], acc[b][1], acc[b][2], acc[b][3]);
-                dst[1] = make_float4(acc[b][4], acc[b][5], acc[b][6], acc[b][7]);
-                dst[2] = make_float4(acc[b][8], acc[b][9], acc[b][10], acc[b][11]);
-            }
+            float4* q = reinterpret_cast<float4*>(dst + 48 * b + 12 * kg);
+            q[0] = make_float4(acc[b][0], acc[b][1], acc[b][2], acc[b][3]);
+            q[1] = make_float4(acc[b][4], acc[b][5], acc[b][6], acc[b][7]);
+            q[2] = make_float4(acc[b][8], acc[b][9], acc[b][10], acc[b][11]);
         }
-        // coefficients beyond the three 16-blocks are never used: zero gradient
-        for (int q = 36 + kg; q < 3 * M / 4; q += 4) row[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    } else {
-#pragma unroll
-        for (int b = 0; b < 3; ++b) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = 16 * b + 4 * kg + j;
-                if (c >= M) continue;
-                float* dst = (c < m0) ? a.out0 + ((size_t)idx * m0 + c) * 3 : a.out1 + ((size_t)idx * (M - m0) + (c - m0)) * 3;
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) dst[ch] = a.accumulate ? dst[ch] + acc[b][3 * j + ch] : acc[b][3 * j + ch];
-            }
-        }
-        if (!a.accumulate)
-            for (int c = 48 + kg; c < M; c += 4) {
-                float* dst = (c < m0) ? a.out0 + ((size_t)idx * m0 + c) * 3 : a.out1 + ((size_t)idx * (M - m0) + (c - m0)) * 3;
-                dst[0] = dst[1] = dst[2] = 0.f;
-            }
+    }
+    __syncthreads();
+    for (int r = warp; r < SO_ROWS; r += 4) {
+        const int kr = blockIdx.x * SO_ROWS + r;
+        if (kr >= a.K) break;
+        store_sh_row(a, (size_t)a.union_idx[kr], &rowbuf[r][0], lane);
     }
 }
 
@@ -885,8 +898,8 @@ cudaError_t launch_sh_outer_sum(const ShSumParams& p, cudaStream_t stream) {
     if (p.P <= 0) return cudaSuccess;
     if ((long long)p.K * p.V > 0)
         sh_outer_dir_kernel<<<(unsigned)(((long long)p.K * p.V + 255) / 256), 256, 0, stream>>>(p);
-    const int union_blocks = (int)((4ll * p.K + 127) / 128);
-    const int zero_blocks = (int)((4ll * p.P + 127) / 128);
+    const int union_blocks = (int)(((long long)p.K + SO_ROWS - 1) / SO_ROWS);
+    const int zero_blocks = (int)(((long long)p.P + 127) / 128);
     sh_outer_sum_kernel<<<(unsigned)(union_blocks + zero_blocks), 128, 0, stream>>>(p, union_blocks);
     return cudaGetLastError();
 }
