@@ -503,7 +503,7 @@ int fdgs_l1_ssim_backward(const float* x, const float* y, int C, int H, int W, c
 
 int fdgs_adam_step(int n, float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
                    const int* widths, const float* lrs, long long P, const long long* rows, long long num_rows, long long step,
-                   float beta1, float beta2, float eps, int zero_grad, void* stream_v) {
+                   double beta1, double beta2, double eps, int zero_grad, void* stream_v) {
     g_last_error.clear();
     if (n < 0 || n > FDGS_MAX_PACK || P < 0 || step < 1 || (rows && num_rows < 0))
         return fail(FDGS_ERR_INVALID_ARG, "bad tensor count / row count / step");
@@ -511,14 +511,14 @@ int fdgs_adam_step(int n, float* const* params, float* const* grads, float* cons
     if (!params || !grads || !exp_avg || !exp_avg_sq || !widths || !lrs) return fail(FDGS_ERR_INVALID_ARG, "null argument");
     float step_sizes[FDGS_MAX_PACK];
     // bias corrections in double on the host, like torch.optim.Adam's single-tensor path
-    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
     for (int i = 0; i < n; ++i) {
         if (!params[i] || !grads[i] || !exp_avg[i] || !exp_avg_sq[i] || widths[i] <= 0)
             return fail(FDGS_ERR_INVALID_ARG, "bad tensor table entry");
         step_sizes[i] = (float)((double)lrs[i] / bc1);
     }
-    FDGS_CUDA(fdgs::launch_adam(n, params, grads, exp_avg, exp_avg_sq, widths, step_sizes, rows ? num_rows : P, rows, beta1, beta2,
-                                eps, (float)sqrt(bc2), zero_grad, reinterpret_cast<cudaStream_t>(stream_v)),
+    FDGS_CUDA(fdgs::launch_adam(n, params, grads, exp_avg, exp_avg_sq, widths, step_sizes, rows ? num_rows : P, rows, (float)(1.0 - beta1),
+                                (float)beta2, (float)(1.0 - beta2), (float)eps, (float)sqrt(bc2), zero_grad, reinterpret_cast<cudaStream_t>(stream_v)),
               "adam_step");
     g_kernel_launches += 1;
     return FDGS_OK;

@@ -215,8 +215,8 @@ cudaError_t launch_l1_ssim_bwd(const float* x, const float* y, int C, int H, int
                                float lambda_dssim, float* dL_dx, cudaStream_t stream);
 // fused multi-tensor Adam, dense or over listed rows: optim.cu
 cudaError_t launch_adam(int n, float* const* params, float* const* grads, float* const* m, float* const* v, const int* widths,
-                        const float* step_sizes, long long rows, const long long* row_idx, float beta1, float beta2, float eps,
-                        float sqrt_bc2, int zero_grad, cudaStream_t stream);
+                        const float* step_sizes, long long rows, const long long* row_idx, float w1, float beta2, float w2,
+                        float eps, float sqrt_bc2, int zero_grad, cudaStream_t stream);
 // uniform-grid k nearest neighbours: knn.cu
 size_t knn_scratch_bytes(int n);
 cudaError_t launch_knn(int n, int k, const float* xyz, char* scratch, int* idx, float* dist2, cudaStream_t stream);

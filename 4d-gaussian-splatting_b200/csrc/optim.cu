@@ -32,7 +32,7 @@ struct AdamTable {
 
 template <bool SPARSE>
 __global__ void __launch_bounds__(256) adam_kernel(const AdamTable tb, long long rows, const long long* __restrict__ row_idx,
-                                                   float beta1, float beta2, float eps, float sqrt_bc2, int zero_grad) {
+                                                   float w1, float beta2, float w2, float eps, float sqrt_bc2, int zero_grad) {
     const int t = blockIdx.y;
     const int w = tb.width[t];
     float* __restrict__ P = tb.param[t];
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamTable tb, long long
     float* __restrict__ M = tb.m[t];
     float* __restrict__ V = tb.v[t];
     const float ss = tb.step_size[t];
-    const float w1 = 1.f - beta1, w2 = 1.f - beta2;
+    // w1 = (float)(1 - beta1), w2 = (float)(1 - beta2) formed in DOUBLE on the host, like the Python scalars torch passes
     const long long total = rows * w;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         long long e = i;
@@ -63,8 +63,8 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamTable tb, long long
 }  // namespace
 
 cudaError_t launch_adam(int n, float* const* params, float* const* grads, float* const* m, float* const* v, const int* widths,
-                        const float* step_sizes, long long rows, const long long* row_idx, float beta1, float beta2, float eps,
-                        float sqrt_bc2, int zero_grad, cudaStream_t stream) {
+                        const float* step_sizes, long long rows, const long long* row_idx, float w1, float beta2, float w2,
+                        float eps, float sqrt_bc2, int zero_grad, cudaStream_t stream) {
     if (n <= 0 || rows <= 0) return cudaSuccess;
     AdamTable tb;
     long long widest = 1;
@@ -76,8 +76,8 @@ cudaError_t launch_adam(int n, float* const* params, float* const* grads, float*
     long long blocks = (widest + 255) / 256;
     if (blocks > device_sm_count() * 16) blocks = device_sm_count() * 16;
     dim3 grid((unsigned)blocks, (unsigned)n, 1);
-    if (row_idx) adam_kernel<true><<<grid, 256, 0, stream>>>(tb, rows, row_idx, beta1, beta2, eps, sqrt_bc2, zero_grad);
-    else adam_kernel<false><<<grid, 256, 0, stream>>>(tb, rows, nullptr, beta1, beta2, eps, sqrt_bc2, zero_grad);
+    if (row_idx) adam_kernel<true><<<grid, 256, 0, stream>>>(tb, rows, row_idx, w1, beta2, w2, eps, sqrt_bc2, zero_grad);
+    else adam_kernel<false><<<grid, 256, 0, stream>>>(tb, rows, nullptr, w1, beta2, w2, eps, sqrt_bc2, zero_grad);
     return cudaGetLastError();
 }
 

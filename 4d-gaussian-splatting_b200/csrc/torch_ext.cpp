@@ -538,7 +538,7 @@ void AdamStep(std::vector<torch::Tensor> params, std::vector<torch::Tensor> grad
     cudaStream_t stream = c10::cuda::getCurrentCUDAStream().stream();
     check(fdgs_adam_step((int)n, p.data(), g.data(), m.data(), v.data(), widths.data(), lr.data(), P,
                          sparse ? reinterpret_cast<const long long*>(rows.data_ptr<int64_t>()) : nullptr, sparse ? rows.numel() : 0,
-                         step, (float)beta1, (float)beta2, (float)eps, zero_grad, (void*)stream),
+                         step, beta1, beta2, eps, zero_grad, (void*)stream),
           "adam_step");
 }
 

@@ -275,12 +275,14 @@ int fdgs_l1_ssim_backward(const float* x, const float* y, int C, int H, int W, c
 
 /* Fused multi-tensor Adam step (reference: torch.optim.Adam(eps=1e-15) over the parameter groups of
  * scene/gaussian_model.py:331-357, stepped at train.py:248-249).  n <= FDGS_MAX_PACK tensors [P, widths[i]] (device),
- * one learning rate each; `step` is the 1-based step count (bias correction).  rows = NULL: every row (torch's dense
+ * one learning rate each; `step` is the 1-based step count (bias correction).  beta1 / beta2 / eps are DOUBLES like the
+ * Python floats torch receives: the weights 1 - beta are formed in double and then rounded to fp32 (1 - 0.999 in fp32
+ * arithmetic is 1.3e-5 off 0.001f).  rows = NULL: every row (torch's dense
  * semantics); otherwise only the `num_rows` listed rows are touched (sparse Adam over the rendered Gaussians).
  * zero_grad != 0 clears the gradient elements it consumed. */
 int fdgs_adam_step(int n, float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
                    const int* widths, const float* lrs, long long P, const long long* rows, long long num_rows,
-                   long long step, float beta1, float beta2, float eps, int zero_grad, void* stream);
+                   long long step, double beta1, double beta2, double eps, int zero_grad, void* stream);
 
 /* k nearest neighbours (k <= 32) of every point among the same n points, squared distances ascending, the point
  * itself first (reference: pointops2 knnquery, pointops2/src/knnquery/knnquery_cuda_kernel.cu:65-107, as called by

@@ -43,6 +43,23 @@ except Exception as e:
 PY
     done
   done
+  for impl in ours reference; do
+    timeout 600 python bench.py --workload cfg4 --rigid --impl $impl --steps 20 --warmup 5 --no-cpu-baseline \
+        > $OUT/${TAG}_cfg4rigid_${impl}.json 2> $OUT/${TAG}_cfg4rigid_${impl}.err
+    timeout 600 python bench.py --workload train3 --impl $impl --steps 10 --warmup 3 --no-cpu-baseline \
+        > $OUT/${TAG}_train3_${impl}.json 2> $OUT/${TAG}_train3_${impl}.err
+    python - <<PY
+import json
+for wl in ("cfg4rigid", "train3"):
+    try:
+        d = json.load(open("$OUT/${TAG}_%s_${impl}.json" % wl))
+        print(wl, "$impl", d["value"], d["unit"], "ms/step", d["ms_per_step"], d.get("phase_ms"))
+    except Exception as e:
+        print(wl, "$impl FAILED", e); print(open("$OUT/${TAG}_%s_${impl}.err" % wl).read()[-1500:])
+PY
+  done
+  timeout 600 python tools/neighbours_bench.py > $OUT/${TAG}_neighbours.md 2> $OUT/${TAG}_neighbours.err
+  tail -40 $OUT/${TAG}_neighbours.md; tail -3 $OUT/${TAG}_neighbours.err
   # cfg1 once more with the CPU baselines (exact cfg1 on the host cores)
   timeout 600 python bench.py --workload cfg1 --steps 20 --warmup 5 > $OUT/${TAG}_cfg1_ours_cpu.json 2> $OUT/${TAG}_cfg1_ours_cpu.err
 fi
