@@ -333,12 +333,15 @@ struct __align__(16) B2Warp {
     float w[B2_COLS][B2_LD];
     float mom[B2_COLS][8];
 };
-template <int STAGES, bool ACOL_SMEM>
+template <int STAGES, bool ACOL_SMEM, bool AUX>
 struct __align__(128) B2Smem {
     StageRec recs[STAGES][B2_BATCH];
     B2Warp warp[B2_WARPS];
     float amom[8][32];      // A fragments of the moment tile (identical for every warp): [2 s + h][lane]
-    float acol[ACOL_SMEM ? B2_WARPS : 1][8][32];   // A fragments of the colour tile (per warp) when not kept in registers
+    // A fragments of the a1-weighted tile (per warp) when not kept in registers.  !AUX: [2 s + h][lane], rows 0..2 =
+    // hi parts of the colour gradient, rows 4..6 = lo parts (rows 8..15 of the m16 tile are zero).  AUX: [4 s + 2 h + part][lane],
+    // rows 0..5 = hi parts of { colour r, g, b, depth, flow x, flow y } gradients (part 0), rows 8..13 = their lo parts (part 1).
+    float acol[ACOL_SMEM ? B2_WARPS : 1][AUX ? 16 : 8][32];
     uint64_t full[STAGES];
     uint64_t empty[STAGES];
     unsigned int nmax;
@@ -362,15 +365,22 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a2
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void mma_tf32_full(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xffffe000u; }
 // the tensor core reads only the upper 19 bits of a tf32 operand, so the remainder needs no masking
 __device__ __forceinline__ uint32_t tf32_lo(float x, uint32_t hi) { return __float_as_uint(x - __uint_as_float(hi)); }
 
-template <int STAGES, bool ACOL_SMEM>
-__global__ void __launch_bounds__(B2_THREADS, ACOL_SMEM ? 4 : 3) blend_bwd2_kernel(const BlendBwdParams p) {
+template <int STAGES, bool ACOL_SMEM, bool AUX>
+__global__ void __launch_bounds__(B2_THREADS, (ACOL_SMEM && !AUX) ? 4 : 3) blend_bwd2_kernel(const BlendBwdParams p) {
+    static_assert(!AUX || ACOL_SMEM, "the AUX instantiation keeps its A fragments in shared memory");
     constexpr int B2_STAGES = STAGES;
     extern __shared__ __align__(128) unsigned char b2_smem_raw[];
-    B2Smem<STAGES, ACOL_SMEM>& sm = *reinterpret_cast<B2Smem<STAGES, ACOL_SMEM>*>(b2_smem_raw);
+    B2Smem<STAGES, ACOL_SMEM, AUX>& sm = *reinterpret_cast<B2Smem<STAGES, ACOL_SMEM, AUX>*>(b2_smem_raw);
     const int tile = blockIdx.y * p.grid_x + blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wx0 = blockIdx.x * TILE_X + (warp & 1) * 8;
@@ -417,11 +427,18 @@ __global__ void __launch_bounds__(B2_THREADS, ACOL_SMEM ? 4 : 3) blend_bwd2_kern
     const float T_final = inside ? p.final_T[pix_id] : 0.f;
     float T = T_final;
     float acc_c0 = 0.f, acc_c1 = 0.f, acc_c2 = 0.f;
+    float acc_f0 = 0.f, acc_f1 = 0.f, acc_d = 0.f, acc_m = 0.f;   // AUX only
     float gp0 = 0.f, gp1 = 0.f, gp2 = 0.f;
+    float gf0 = 0.f, gf1 = 0.f, gd = 0.f, gm = 0.f;               // AUX only
     if (inside) {
         gp0 = p.dL_dpix[0 * HW + pix_id];
         gp1 = p.dL_dpix[1 * HW + pix_id];
         gp2 = p.dL_dpix[2 * HW + pix_id];
+        if (AUX) {
+            if (p.dL_dpix_flow) { gf0 = p.dL_dpix_flow[0 * HW + pix_id]; gf1 = p.dL_dpix_flow[1 * HW + pix_id]; }
+            if (p.dL_depths) gd = p.dL_depths[pix_id];
+            if (p.dL_masks) gm = p.dL_masks[pix_id];
+        }
     }
     const float tb = -T_final * (p.background[0] * gp0 + p.background[1] * gp1 + p.background[2] * gp2);
 
@@ -438,11 +455,23 @@ __global__ void __launch_bounds__(B2_THREADS, ACOL_SMEM ? 4 : 3) blend_bwd2_kern
             const float v0 = __shfl_sync(0xffffffffu, gp0, srcl);
             const float v1 = __shfl_sync(0xffffffffu, gp1, srcl);
             const float v2 = __shfl_sync(0xffffffffu, gp2, srcl);
-            const int ch = fg & 3;
-            const float val = (ch == 0) ? v0 : (ch == 1) ? v1 : (ch == 2) ? v2 : 0.f;
-            const uint32_t hi = tf32_hi(val);
-            acol[s][h] = (fg < 4) ? hi : tf32_lo(val, hi);
-            if (ACOL_SMEM) sm.acol[warp][2 * s + h][lane] = __uint_as_float(acol[s][h]);
+            if (AUX) {
+                // row fg of the 6 weights; hi part -> rows 0..7 (a0 / a2), lo part -> rows 8..15 (a1 / a3)
+                const float v3 = __shfl_sync(0xffffffffu, gd, srcl);
+                const float v4 = __shfl_sync(0xffffffffu, gf0, srcl);
+                const float v5 = __shfl_sync(0xffffffffu, gf1, srcl);
+                const float val = (fg == 0) ? v0 : (fg == 1) ? v1 : (fg == 2) ? v2 : (fg == 3) ? v3 : (fg == 4) ? v4 : (fg == 5) ? v5 : 0.f;
+                const uint32_t hi = tf32_hi(val);
+                sm.acol[warp][(AUX ? 4 : 0) * s + 2 * h + 0][lane] = __uint_as_float(hi);
+                sm.acol[warp][(AUX ? 4 : 0) * s + 2 * h + 1][lane] = __uint_as_float(tf32_lo(val, hi));
+                acol[s][h] = 0u;
+            } else {
+                const int ch = fg & 3;
+                const float val = (ch == 0) ? v0 : (ch == 1) ? v1 : (ch == 2) ? v2 : 0.f;
+                const uint32_t hi = tf32_hi(val);
+                acol[s][h] = (fg < 4) ? hi : tf32_lo(val, hi);
+                if (ACOL_SMEM) sm.acol[warp][2 * s + h][lane] = __uint_as_float(acol[s][h]);
+            }
             const float ku = (float)(ft + 4 * h) - 3.5f, kv = (float)s - 1.5f;
             const float mono = (fg == 0) ? 1.f : (fg == 1) ? ku : (fg == 2) ? kv : (fg == 3) ? ku * ku
                              : (fg == 4) ? ku * kv : (fg == 5) ? kv * kv : 0.f;
@@ -465,22 +494,45 @@ __global__ void __launch_bounds__(B2_THREADS, ACOL_SMEM ? 4 : 3) blend_bwd2_kern
             const float x0 = ws.a1[fg][8 * s + ft], x1 = ws.a1[fg][8 * s + ft + 4];
             const float y0 = ws.w[fg][8 * s + ft], y1 = ws.w[fg][8 * s + ft + 4];
             const uint32_t x0h = tf32_hi(x0), x1h = tf32_hi(x1), y0h = tf32_hi(y0), y1h = tf32_hi(y1);
-            const uint32_t ac0 = ACOL_SMEM ? __float_as_uint(sm.acol[warp][2 * s][lane]) : acol[s][0];
-            const uint32_t ac1 = ACOL_SMEM ? __float_as_uint(sm.acol[warp][2 * s + 1][lane]) : acol[s][1];
-            mma_tf32(c1, ac0, ac1, x0h, x1h);
-            mma_tf32(c1, ac0, ac1, tf32_lo(x0, x0h), tf32_lo(x1, x1h));
+            if (AUX) {
+                const uint32_t f0 = __float_as_uint(sm.acol[warp][(AUX ? 4 : 0) * s + 0][lane]);   // a0: hi, pixels ft
+                const uint32_t f1 = __float_as_uint(sm.acol[warp][(AUX ? 4 : 0) * s + 1][lane]);   // a1: lo, pixels ft
+                const uint32_t f2 = __float_as_uint(sm.acol[warp][(AUX ? 4 : 0) * s + 2][lane]);   // a2: hi, pixels ft + 4
+                const uint32_t f3 = __float_as_uint(sm.acol[warp][(AUX ? 4 : 0) * s + 3][lane]);   // a3: lo, pixels ft + 4
+                mma_tf32_full(c1, f0, f1, f2, f3, x0h, x1h);
+                mma_tf32_full(c1, f0, f1, f2, f3, tf32_lo(x0, x0h), tf32_lo(x1, x1h));
+            } else {
+                const uint32_t ac0 = ACOL_SMEM ? __float_as_uint(sm.acol[warp][2 * s][lane]) : acol[s][0];
+                const uint32_t ac1 = ACOL_SMEM ? __float_as_uint(sm.acol[warp][2 * s + 1][lane]) : acol[s][1];
+                mma_tf32(c1, ac0, ac1, x0h, x1h);
+                mma_tf32(c1, ac0, ac1, tf32_lo(x0, x0h), tf32_lo(x1, x1h));
+            }
             const uint32_t am0 = __float_as_uint(sm.amom[2 * s][lane]), am1 = __float_as_uint(sm.amom[2 * s + 1][lane]);
             mma_tf32(c2, am0, am1, y0h, y1h);
             mma_tf32(c2, am0, am1, tf32_lo(y0, y0h), tf32_lo(y1, y1h));
         }
         // c1[0], c1[1]: row fg of the colour tile for columns 2 ft, 2 ft + 1; add the lo rows (fg + 4) to the hi rows
-        c1[0] += __shfl_xor_sync(0xffffffffu, c1[0], 16);
-        c1[1] += __shfl_xor_sync(0xffffffffu, c1[1], 16);
+        if (AUX) {
+            // rows fg (hi) and fg + 8 (lo) of the a1-weighted tile sit in the same lane
+            c1[0] += c1[2];
+            c1[1] += c1[3];
+        } else {
+            c1[0] += __shfl_xor_sync(0xffffffffu, c1[0], 16);
+            c1[1] += __shfl_xor_sync(0xffffffffu, c1[1], 16);
+        }
         if (fg < 6) {
             ws.mom[2 * ft][fg] = c2[0];
             ws.mom[2 * ft + 1][fg] = c2[1];
         }
-        if (fg < 3) {
+        if (AUX) {
+            if (fg < 6) {
+                // rows: colour r, g, b -> dL_dcolor; depth -> dL_dmean2D.z (backward.cu:1091); flow x, y -> dL_dflows
+                float* const base = (fg < 3) ? p.dL_dcolor + fg : (fg == 3) ? p.dL_dmean2D + 2 : p.dL_dflows + (fg - 4);
+                const size_t mul = (fg < 4) ? 3 : 2;
+                if (2 * ft < cols) atomicAdd(base + (size_t)__float_as_uint(ws.a1[2 * ft][35]) * mul, c1[0]);
+                if (2 * ft + 1 < cols) atomicAdd(base + (size_t)__float_as_uint(ws.a1[2 * ft + 1][35]) * mul, c1[1]);
+            }
+        } else if (fg < 3) {
             if (2 * ft < cols) atomicAdd(p.dL_dcolor + (size_t)__float_as_uint(ws.a1[2 * ft][35]) * 3 + fg, c1[0]);
             if (2 * ft + 1 < cols) atomicAdd(p.dL_dcolor + (size_t)__float_as_uint(ws.a1[2 * ft + 1][35]) * 3 + fg, c1[1]);
         }
@@ -580,6 +632,19 @@ __global__ void __launch_bounds__(B2_THREADS, ACOL_SMEM ? 4 : 3) blend_bwd2_kern
                         acc_c0 = fmaf(alpha, d0, acc_c0);
                         acc_c1 = fmaf(alpha, d1, acc_c1);
                         acc_c2 = fmaf(alpha, d2, acc_c2);
+                        if (AUX) {
+                            // flow / depth / alpha-image recurrences, backward.cu:1078-1102
+                            const float2 fl = *reinterpret_cast<const float2*>(&rec->q3);
+                            const float e0 = fl.x - acc_f0, e1 = fl.y - acc_f1, dd = s2.w - acc_d, dm = 1.0f - acc_m;
+                            dL_dalpha = fmaf(e0, gf0, dL_dalpha);
+                            dL_dalpha = fmaf(e1, gf1, dL_dalpha);
+                            dL_dalpha = fmaf(dd, gd, dL_dalpha);
+                            dL_dalpha = fmaf(dm, gm, dL_dalpha);
+                            acc_f0 = fmaf(alpha, e0, acc_f0);
+                            acc_f1 = fmaf(alpha, e1, acc_f1);
+                            acc_d = fmaf(alpha, dd, acc_d);
+                            acc_m = fmaf(alpha, dm, acc_m);
+                        }
                         dL_dalpha = fmaf(tb, rom, dL_dalpha * T);
                         wv = G_c * dL_dalpha;
                     }
@@ -609,23 +674,32 @@ __global__ void __launch_bounds__(B2_THREADS, ACOL_SMEM ? 4 : 3) blend_bwd2_kern
 
 }  // namespace
 
-bool blend_bwd_is_raw(const BlendBwdParams& p) {
-    // colour-only upstream gradient: the v2 kernel, which leaves RAW moment sums in dL_dmean2D.xy /
-    // dL_dconic / dL_dopacity for geom_bwd_kernel to finish (PreprocessBwdParams::blend_raw)
+bool blend_bwd_is_raw(const BlendBwdParams&) {
+    // the v2 kernels leave RAW moment sums in dL_dmean2D.xy / dL_dconic / dL_dopacity for geom_bwd_kernel to finish
+    // (PreprocessBwdParams::blend_raw); FDGS_BLEND_BWD_V1 selects the shuffle-reduction kernels (kept for comparison)
     static const bool force_v1 = getenv("FDGS_BLEND_BWD_V1") != nullptr;
-    return !force_v1 && !p.dL_depths && !p.dL_masks && !p.dL_dpix_flow;
+    return !force_v1;
 }
 
 cudaError_t launch_blend_bwd(const BlendBwdParams& p, cudaStream_t stream) {
     dim3 grid(p.grid_x, p.grid_y, 1);
+    const bool aux = p.dL_depths || p.dL_masks || p.dL_dpix_flow;
     if (blend_bwd_is_raw(p)) {
-        // colour fragments in shared memory + 3 stages: 64 registers, 53 KB -> 4 CTAs / SM.  (Keeping them in
-        // registers costs 80 registers -> 3 CTAs / SM and measured 8 % slower.)
-        static PerDeviceOnce once;
-        cudaError_t e = ensure_dynamic_smem(blend_bwd2_kernel<3, true>, (int)sizeof(B2Smem<3, true>), once);
-        if (e != cudaSuccess) return e;
-        blend_bwd2_kernel<3, true><<<grid, B2_THREADS, sizeof(B2Smem<3, true>), stream>>>(p);
-    } else if (!p.dL_depths && !p.dL_masks && !p.dL_dpix_flow) {
+        if (!aux) {
+            // colour fragments in shared memory + 3 stages: 64 registers, 53 KB -> 4 CTAs / SM.  (Keeping them in
+            // registers costs 80 registers -> 3 CTAs / SM and measured 8 % slower.)
+            static PerDeviceOnce once;
+            cudaError_t e = ensure_dynamic_smem(blend_bwd2_kernel<3, true, false>, (int)sizeof(B2Smem<3, true, false>), once);
+            if (e != cudaSuccess) return e;
+            blend_bwd2_kernel<3, true, false><<<grid, B2_THREADS, sizeof(B2Smem<3, true, false>), stream>>>(p);
+        } else {
+            // upstream gradients for the depth / alpha / flow images too: 6 a1-weighted rows (16-row A tile), 3 CTAs / SM
+            static PerDeviceOnce once_aux;
+            cudaError_t e = ensure_dynamic_smem(blend_bwd2_kernel<3, true, true>, (int)sizeof(B2Smem<3, true, true>), once_aux);
+            if (e != cudaSuccess) return e;
+            blend_bwd2_kernel<3, true, true><<<grid, B2_THREADS, sizeof(B2Smem<3, true, true>), stream>>>(p);
+        }
+    } else if (!aux) {
         blend_bwd_kernel<false><<<grid, BB_THREADS, 0, stream>>>(p);
     } else {
         blend_bwd_kernel<true><<<grid, BB_THREADS, 0, stream>>>(p);

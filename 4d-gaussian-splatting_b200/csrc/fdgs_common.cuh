@@ -314,12 +314,15 @@ __device__ __forceinline__ bool rect_may_contribute(float x0, float y0, float A,
     const float q2 = 0.5f * (A * tx * tx + C * ddy * ddy) + B * tx * ddy;
     // if the centre is outside in one axis only, only that axis' edge applies; inside: q = 0
     float qmin = (ddx != 0.f) ? ((ddy != 0.f) ? fminf(q1, q2) : q1) : ((ddy != 0.f) ? q2 : 0.f);
-    // thin, rotated Gaussians far from their centre: the three terms of q are large and cancel, their fp32 rounding
-    // error can exceed the slack -> never cull on such a value (the blend loop decides those pairs exactly)
+    // thin, rotated Gaussians far from their centre: the three terms of q are large and cancel, so the fp32 rounding
+    // error of q -- and of the blend loop's own power -- grows with their magnitude.  Both are bounded by ~6 roundings
+    // of 2^-24 each relative to `mag`; the cull keeps 2e-6 * mag of extra slack, i.e. it only rejects when even the
+    // worst-case rounding leaves q above the cut.  (A fixed "never cull above mag = 128" guard was measured to triple
+    // the survivors of cfg3: an ordinary 1-pixel Gaussian 12 pixels away already has A ddx^2 = 144.)
     const float mag = fmaxf(fabsf(A * ddx * ddx) + fabsf(C * ty * ty) + 2.f * fabsf(B * ddx * ty),
                             fabsf(A * tx * tx) + fabsf(C * ddy * ddy) + 2.f * fabsf(B * tx * ddy));
-    if (!(mag < 128.f) && pmin < 3.0e38f) return true;
-    return !(qmin > -pmin + 1e-3f);   // also true for pmin = -inf, false for pmin = +inf
+    // also true for pmin = -inf (and for a non-finite mag), false for pmin = +inf
+    return !(qmin > -pmin + 1e-3f + 2.0e-6f * mag);
 }
 
 // ---- mbarrier / bulk-copy (TMA 1-D) PTX wrappers ----------------------------------------------

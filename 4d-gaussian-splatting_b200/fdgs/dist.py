@@ -215,6 +215,8 @@ class ViewParallelStep:
         self._outer_sum_fn = outer_sum_fn
         self.info: Dict[str, object] = {}
         self.profile = False            # True: CUDA events around the phases of finish() -> info["phase_ms"] (one sync)
+        self.profile_serial = False     # with profile: wait for every collective where it is launched (no overlap), so
+                                        # that the phases are the collectives' own durations (bus-bandwidth figures)
         self._marks = []
         self.expected_views = expected_views
         self._fwd_radii = None
@@ -324,25 +326,13 @@ class ViewParallelStep:
         self.info = {"K": K, "union_fraction": K / max(P, 1), "geometry_path": "rows" if sparse_ok else "dense",
                      "views_local": len(self.views), "early_union": self._early is not None}
 
-        # -- geometry bucket + the two SUM statistics: one flat buffer, one collective
-        if world > 1:
-            bucket = grads + [st.grad_norm_sum, st.visibility_count]
-            if sparse_ok:
-                if K > 0:
-                    flat = _pack(bucket, idx)
-                    self._mark("geometry_pack")
-                    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-                    self._mark("geometry_allreduce")
-                    _unpack(flat, bucket, idx)
-                    self._mark("geometry_unpack")
-                    self.info["geometry_allreduce_bytes"] = int(flat.numel() * 4)
-            else:
-                works = [dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group, async_op=True) for g in bucket]
-                for w in works:
-                    w.wait()
-
-        # -- SH rows: all-gather the colour factors of the union, rebuild + sum locally
-        if have_factors or (self.sh_factors and len(sh_params) > 0 and world > 1):
+        # -- both payloads are packed first, both collectives are launched asynchronously (NCCL runs them in issue
+        #    order on its own stream: the small factor all-gather, then the geometry all-reduce), and the SH
+        #    reconstruction -- the longest phase, needing only the factors -- runs on the compute stream WHILE the
+        #    geometry bucket is being reduced; the bucket is scattered back afterwards
+        want_sh = have_factors or (self.sh_factors and len(sh_params) > 0 and world > 1)
+        local = table = None
+        if want_sh:
             assert len(sh_params) in (1, 2), "sh_params: the [P,M,3] SH tensor or (features_dc, features_rest)"
             v_local = len(self.views)
             if views_per_rank is None:
@@ -360,12 +350,36 @@ class ViewParallelStep:
                 local[v, meta_off] = rec.timestamp
                 local[v, meta_off + 1:meta_off + 4] = rec.campos.reshape(3).to(local.dtype)
             self._mark("factor_pack")
-            if world > 1:
-                table = torch.empty(world * views_per_rank, stride, dtype=torch.float32, device=union.device)
-                dist.all_gather_into_tensor(table, local, group=group)
+        bucket = grads + [st.grad_norm_sum, st.visibility_count]
+        flat, geo_works = None, []
+        if world > 1 and sparse_ok and K > 0:
+            flat = _pack(bucket, idx)
+            self._mark("geometry_pack")
+            self.info["geometry_allreduce_bytes"] = int(flat.numel() * 4)
+        gather_work = None
+        if want_sh and world > 1:
+            table = torch.empty(world * views_per_rank, stride, dtype=torch.float32, device=union.device)
+            gather_work = dist.all_gather_into_tensor(table, local, group=group, async_op=True)
+            if self.profile_serial:
+                gather_work.wait()
                 self._mark("factor_allgather")
-            else:
-                table = local
+                gather_work = None
+        elif want_sh:
+            table = local
+        if world > 1:
+            if flat is not None:
+                geo_works = [dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True)]
+            elif not sparse_ok:
+                geo_works = [dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group, async_op=True) for g in bucket]
+            if self.profile_serial and geo_works:
+                for w in geo_works:
+                    w.wait()
+                self._mark("geometry_allreduce")
+                geo_works = []
+        if want_sh:
+            if gather_work is not None:
+                gather_work.wait()
+                self._mark("factor_allgather")
             outs = []
             for p in sh_params:
                 if p.grad is None:
@@ -374,6 +388,13 @@ class ViewParallelStep:
             self._outer_sum(table, stride, meta_off, table.shape[0], K, slot_of, outs, idx)
             self._mark("sh_outer_sum")
             self.info.update(views_total=int(table.shape[0]), factor_bytes_per_rank=int(local.numel() * 4))
+        for w in geo_works:
+            w.wait()
+        if geo_works:
+            self._mark("geometry_allreduce_exposed")   # what is left of it after the SH reconstruction
+        if flat is not None:
+            _unpack(flat, bucket, idx)
+            self._mark("geometry_unpack")
         self.views = []
         self._early, self._fwd_radii, self._fwd_count = None, None, 0
         if world > 1:

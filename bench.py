@@ -55,6 +55,11 @@ WORKLOADS = {
                  desc="500k 4D Gaussians, 1352x1014, forward only (no_grad)"),
     "cfg3": dict(cfg="cfg3", mode="fwdbwd", views=1, metric="fwd+bwd Mpixels/s @1352x1014, 2M 4D Gaussians",
                  desc="2M 4D Gaussians, 1352x1014, fwd+bwd, SH degree 3"),
+    # cfg3 with upstream gradients for the depth, alpha and flow images too (losses on them, e.g. lambda_opa_mask > 0,
+    # reference train.py:120-129): the AUX instantiation of the blend backward
+    "cfg3aux": dict(cfg="cfg3", mode="fwdbwd", views=1, aux=True,
+                    metric="fwd+bwd Mpixels/s @1352x1014, 2M 4D Gaussians, colour+depth+alpha+flow gradients",
+                    desc="cfg3 with the loss touching the colour, depth, alpha and flow images"),
     "cfg4": dict(cfg=None, mode="train", views=2, metric="train iterations/s (lego shape: 100k points, 800x800, batch 2)",
                  desc="DNeRF 'lego' shape synthetic init, 800x800, batch of 2 views, L1 + Adam (lambda_rigid = 0)"),
     "cfg5": dict(cfg="cfg5", mode="fwdbwd", views=8, metric="fwd+bwd Mpixels/s @1352x1014, 300k 4D Gaussians, 8 views/step",
@@ -205,6 +210,7 @@ class Runner:
     def __init__(self, wl: Workload, impl: str, world: int, views_total: int):
         self.wl, self.impl, self.world, self.views_total = wl, impl, world, views_total
         self.backward = wl.spec["mode"] == "fwdbwd"
+        self.aux = bool(wl.spec.get("aux"))
         if impl == "ours":
             from gaussian_renderer import GaussianRasterizationSettings, GaussianRasterizer
             self.Settings, self.Rasterizer = GaussianRasterizationSettings, GaussianRasterizer
@@ -222,6 +228,7 @@ class Runner:
             os.environ.get("FDGS_DENSE_ALLREDUCE") is None
         self.exchange_info = None
         self.profile_exchange = False
+        self.profile_serial = False
         # e2e leg: the upstream gradient image of a view is double-buffered on the device and uploaded one step ahead
         # on the copy stream (a data loader prefetching the next ground-truth image); every step still copies its
         # inputs host->device inside the timed region
@@ -258,6 +265,7 @@ class Runner:
             from fdgs.dist import ViewParallelStep
             step = ViewParallelStep(wl.P, wl.device, expected_views=len(wl.view_ids))
             step.profile = self.profile_exchange
+            step.profile_serial = self.profile_serial
             step.__enter__()
         result = None
         try:
@@ -281,6 +289,9 @@ class Runner:
                     if host_inputs:
                         cur.wait_event(ready)
                     loss = (color * G).sum() / self.views_total
+                    if self.aux:
+                        loss = loss + ((depth * G[:depth.shape[0]]).sum() + (alpha * G[1:1 + alpha.shape[0]]).sum() +
+                                       (flow * G[:flow.shape[0]]).sum()) / self.views_total
                     loss.backward()
                     if host_inputs:
                         b = self.g_step & 1
@@ -724,15 +735,23 @@ def main():
         prof = fdgs.profile_read()
         fdgs.profile_enable(False)
         if runner.exchange:
-            # phase table of the gradient exchange (CUDA events inside ViewParallelStep.finish, 3 extra steps)
+            # phase tables of the gradient exchange (CUDA events inside ViewParallelStep.finish, 3 extra steps each):
+            # phase_ms = as the step runs it (geometry all-reduce overlapped with the SH reconstruction: only its exposed
+            # remainder shows); phase_serial_ms = every collective waited for where it is launched (its own duration)
             runner.profile_exchange = True
-            acc = {}
-            for _ in range(3):
-                runner.step(False)
-                for k, v in (runner.exchange_info.get("phase_ms") or {}).items():
-                    acc[k] = acc.get(k, 0.0) + v / 3
+            tables = {}
+            for serial in (False, True):
+                runner.profile_serial = serial
+                acc = {}
+                for _ in range(3):
+                    runner.step(False)
+                    for k, v in (runner.exchange_info.get("phase_ms") or {}).items():
+                        acc[k] = acc.get(k, 0.0) + v / 3
+                tables[serial] = acc
             runner.profile_exchange = False
-            runner.exchange_info = dict(runner.exchange_info, phase_ms=acc)
+            runner.profile_serial = False
+            acc = tables[True]
+            runner.exchange_info = dict(runner.exchange_info, phase_ms=tables[False], phase_serial_ms=tables[True])
             n = eff_world
             ab, gb = runner.exchange_info.get("geometry_allreduce_bytes"), runner.exchange_info.get("factor_bytes_per_rank")
             if n > 1 and ab and acc.get("geometry_allreduce"):

@@ -16,7 +16,7 @@ if has golden; then
   grep -E "golden written|diff=|CONFIG" $OUT/${TAG}_golden.log | tail -40
 fi
 if has tests; then
-  timeout 1500 python -m pytest tests -m gpu -q > $OUT/${TAG}_pytest.log 2>&1
+  timeout 900 python -m pytest tests -m gpu -q --durations=15 > $OUT/${TAG}_pytest.log 2>&1
   echo "pytest exit $?" >> $OUT/${TAG}_pytest.log
   tail -15 $OUT/${TAG}_pytest.log
 fi
@@ -94,7 +94,7 @@ if has sanitize; then
 fi
 if has racecheck; then
   # shared-memory hazards of the forward / both backward kernels (the v2 backward shares per-warp slots across lanes)
-  timeout 1500 compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q \
+  timeout 420 compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q \
       -k "golden and (tiny or ragged) or (colour_only_backward_equals_zero_aux_gradients and small)" > $OUT/${TAG}_racecheck.log 2>&1
   echo "racecheck exit $?" >> $OUT/${TAG}_racecheck.log
   grep -E "RACECHECK SUMMARY|hazard|passed|failed|racecheck exit" $OUT/${TAG}_racecheck.log | tail -8
