@@ -86,10 +86,14 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_pass_kernel(int P, int chunk,
         // Small rectangles (the common case: a ~1.5-pixel-sigma Gaussian touches 1-4 tiles) are walked by their own
         // lane -- no shuffles, no division, the warp runs for max(n) <= BIN_SMALL iterations; only the large ones
         // are spread over the 32 lanes.  The order inside a tile's segment is arbitrary either way (sorted later).
+        // br.w: tile mask of rectangles of up to 32 tiles (bit i = tile i, row-major, takes an instance; all ones when
+        // the preprocess did not cull by tile)
         if (n > 0 && n <= BIN_SMALL) {
             const uint64_t key = SCATTER ? (((uint64_t)br.z << 32) | (uint32_t)(g0 + lane)) : 0ull;
+            uint32_t m = br.w;
             for (int ty = y0; ty < y1; ++ty) {
-                for (int tx = x0; tx < x1; ++tx) {
+                for (int tx = x0; tx < x1; ++tx, m >>= 1) {
+                    if (!(m & 1u)) continue;
                     const uint32_t slot = atomicAdd(&hist[ty * grid_x + tx], 1u);
                     if (SCATTER) keys[slot] = key;
                 }
@@ -101,10 +105,12 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_pass_kernel(int P, int chunk,
             mask &= mask - 1;
             const int bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
             const int bw = __shfl_sync(0xffffffffu, w, src), bn = __shfl_sync(0xffffffffu, n, src);
+            const uint32_t bmask = __shfl_sync(0xffffffffu, br.w, src);
             uint64_t key = 0;
             // key: depth bits (positive floats: integer order == float order) then Gaussian index
             if (SCATTER) key = ((uint64_t)__shfl_sync(0xffffffffu, br.z, src) << 32) | (uint32_t)(g0 + src);
             for (int i = lane; i < bn; i += 32) {
+                if (bn <= 32 && !((bmask >> i) & 1u)) continue;
                 const int ry = i / bw, rx = i - ry * bw;
                 const int t = (by0 + ry) * grid_x + bx0 + rx;
                 const uint32_t slot = atomicAdd(&hist[t], 1u);

@@ -46,6 +46,10 @@ const bool g_trace = getenv("FDGS_TRACE") != nullptr;
 // summation order of the quaternion norm in the raw-parameter entry (fdgs_common.cuh: quat_norm); 0 = ATen's order
 const int g_quat_norm_mode = getenv("FDGS_NORMALIZE_MODE") ? atoi(getenv("FDGS_NORMALIZE_MODE")) : 0;
 
+// tile lists: 1 = only the tiles a Gaussian's alpha >= 1/255 footprint reaches, 0 = the reference's 3-sigma square
+// (include/fdgs.h: fdgs_set_tile_cull)
+std::atomic<int> g_tile_cull{getenv("FDGS_TILE_CULL") ? atoi(getenv("FDGS_TILE_CULL")) : 1};
+
 struct StageTimer {
     cudaEvent_t a = nullptr, b = nullptr;
     int stage;
@@ -285,6 +289,7 @@ int fdgs_forward(const fdgs_forward_args* a, fdgs_alloc_fn geom_alloc, void* geo
         pp.flows = a->flows_precomp;
         pp.out_means3D = a->out_means3D; pp.radii = a->radii; pp.cov3D = geom.cov3D; pp.grec = geom.grec;
         pp.clamped = geom.clamped; pp.tiles_touched = geom.tiles_touched; pp.binrec = geom.binrec;
+        pp.tile_cull = g_tile_cull.load();
         FDGS_STAGE(0, 1, fdgs::launch_preprocess_fwd(pp, stream), "preprocess_fwd");
     }
     // binning: per-tile counts, offsets, ranges and the total instance count R
@@ -578,6 +583,8 @@ int fdgs_profile_read(double ms[FDGS_NUM_STAGES], long long calls[FDGS_NUM_STAGE
 }
 
 long long fdgs_launch_count(void) { return g_kernel_launches.load(); }
+
+int fdgs_set_tile_cull(int mode) { return g_tile_cull.exchange(mode ? 1 : 0); }
 
 int fdgs_debug_export_geom(const char* geom_buffer, int P, float* depths, float* means2D, float* conic_opacity,
                            float* rgb, unsigned char* clamped, unsigned int* tiles_touched, void* stream_v) {

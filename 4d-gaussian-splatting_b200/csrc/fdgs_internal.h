@@ -67,6 +67,7 @@ struct PreprocessFwdParams {
     uint8_t* clamped;       // bit ch set = channel ch was clamped at 0
     uint32_t* tiles_touched;
     uint4* binrec;          // [P] compact bin record of EVERY Gaussian (see launch_bin_count)
+    int tile_cull;          // != 0: list a Gaussian only in the tiles its alpha >= 1/255 footprint reaches (fdgs_set_tile_cull)
 };
 cudaError_t launch_preprocess_fwd(const PreprocessFwdParams& p, cudaStream_t stream);
 cudaError_t launch_debug_activate(int n, const float* log_s, const float* logit, const float* quat, int mode, float* s_out,
@@ -75,7 +76,8 @@ cudaError_t launch_debug_activate(int n, const float* log_s, const float* logit,
 // ---- binning -----------------------------------------------------------------------------------
 // counting sort of the (Gaussian, tile) instances by tile, BIN_CTAS persistent CTAs (binning.cu)
 int bin_ctas();                                 // rows of the [bin_ctas()][num_tiles] count matrix
-// binrec[i] = { x0 | y0 << 16, x1 | y1 << 16, depth bits, 0 }: tile rectangle (empty = not rendered) of Gaussian i
+// binrec[i] = { x0 | y0 << 16, x1 | y1 << 16, depth bits, tile mask }: tile rectangle (empty = not listed anywhere) of
+// Gaussian i; for rectangles of up to 32 tiles bit j of the mask = tile j (row-major) takes an instance
 cudaError_t launch_bin_count(int P, const uint4* binrec, int grid_x, int grid_y, uint32_t* matrix, cudaStream_t stream);
 // matrix -> per-CTA column prefixes; tile_offset / ranges; info[0] = total instances R, info[1] = largest tile
 cudaError_t launch_tile_scan(int num_tiles, uint32_t* matrix, uint32_t* tile_total, uint32_t* tile_offset, uint2* ranges,

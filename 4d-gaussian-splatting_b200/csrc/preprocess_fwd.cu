@@ -401,10 +401,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 5) preprocess_fwd_kernel(const Pr
     if (in_range) {
         a.radii[idx] = visible ? radius : 0;
         a.tiles_touched[idx] = visible ? tiles : 0u;
-        // compact record for the binning passes: tile rectangle (empty when not rendered) + depth bits
-        a.binrec[idx] = visible ? make_uint4((uint32_t)rx0 | ((uint32_t)ry0 << 16), (uint32_t)rx1 | ((uint32_t)ry1 << 16),
-                                             __float_as_uint(depth), 0u)
-                                : make_uint4(0u, 0u, 0u, 0u);
+        uint4 brec = make_uint4(0u, 0u, 0u, 0u);
         if (visible) {
             a.clamped[idx] = clamp_bits;
             // The 64-byte record every (tile, Gaussian) instance copies (binning.cu).  Besides the
@@ -426,6 +423,49 @@ __global__ void __launch_bounds__(PRE_THREADS, 5) preprocess_fwd_kernel(const Pr
                 sba = -cony / conx;
                 if (!(fabsf(sbc) <= 3.0e38f) || !(fabsf(sba) <= 3.0e38f)) { pmin = -INFINITY; sbc = sba = 0.f; }
             }
+            // Compact record for the binning passes: tile rectangle + depth bits + tile mask.  The reference lists the
+            // Gaussian in every tile of the square of half-width ceil(3 sigma_max) around its centre
+            // (auxiliary.h:46-59 getRect) although only the pixels of the alpha >= 1/255 ellipse can ever blend it;
+            // with tile_cull the rectangle is shrunk to the tiles the ellipse's bounding box touches and, for
+            // rectangles of up to 32 tiles, bit i of the mask says whether tile i (row-major inside the shrunk
+            // rectangle) can contain such a pixel at all -- the same exact, conservative test the blend kernels apply
+            // per 8x4 warp rectangle.  Instances dropped here are instances no pixel would have blended: the image,
+            // every other output and every gradient are unchanged; only the private tile lists get shorter.
+            int tx0 = rx0, ty0 = ry0, tx1 = rx1, ty1 = ry1;
+            uint32_t tmask = 0xffffffffu;
+            if (a.tile_cull) {
+                if (pmin == INFINITY) {
+                    tx1 = tx0; ty1 = ty0;
+                } else if (pmin > -3.0e38f) {
+                    // bounding box of { d : 0.5 d^T Q d <= -pmin }: half extents sqrt(2 q C / det), sqrt(2 q A / det)
+                    const float q2 = -2.f * pmin;
+                    const float ex = sqrtf(q2 * conz / cdet) * 1.0001f + 0.01f;
+                    const float ey = sqrtf(q2 * conx / cdet) * 1.0001f + 0.01f;
+                    if (ex <= 1.0e6f && ey <= 1.0e6f && fabsf(px) <= 1.0e6f && fabsf(py) <= 1.0e6f) {
+                        // pixel centres are the integers: pixel p lies in tile floor(p / 16)
+                        tx0 = max(rx0, (int)floorf((px - ex) * (1.0f / TILE_X)));
+                        tx1 = min(rx1, (int)floorf((px + ex) * (1.0f / TILE_X)) + 1);
+                        ty0 = max(ry0, (int)floorf((py - ey) * (1.0f / TILE_Y)));
+                        ty1 = min(ry1, (int)floorf((py + ey) * (1.0f / TILE_Y)) + 1);
+                        if (tx1 <= tx0 || ty1 <= ty0) { tx1 = tx0; ty1 = ty0; }
+                        const int tw = tx1 - tx0, tn = tw * (ty1 - ty0);
+                        if (tn > 0 && tn <= 32) {
+                            tmask = 0u;
+                            int cx = tx0, cy = ty0;
+                            for (int i = 0; i < tn; ++i) {
+                                const float bx0 = (float)(cx * TILE_X), by0 = (float)(cy * TILE_Y);
+                                if (rect_may_contribute(px, py, conx, cony, conz, pmin, sbc, sba, bx0, bx0 + (float)(TILE_X - 1), by0,
+                                                        by0 + (float)(TILE_Y - 1)))
+                                    tmask |= 1u << i;
+                                if (++cx == tx1) { cx = tx0; ++cy; }
+                            }
+                            if (tmask == 0u) { tx1 = tx0; ty1 = ty0; }
+                        }
+                    }
+                }
+            }
+            if (tx1 > tx0 && ty1 > ty0)
+                brec = make_uint4((uint32_t)tx0 | ((uint32_t)ty0 << 16), (uint32_t)tx1 | ((uint32_t)ty1 << 16), __float_as_uint(depth), tmask);
             const float fx = a.flows ? a.flows[2 * idx + 0] : 0.f, fy = a.flows ? a.flows[2 * idx + 1] : 0.f;
             float4* dst = reinterpret_cast<float4*>(a.grec + idx);
             dst[0] = make_float4(px, py, pmin, __uint_as_float((uint32_t)idx));
@@ -433,6 +473,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 5) preprocess_fwd_kernel(const Pr
             dst[2] = make_float4(rgb[0], rgb[1], rgb[2], depth);
             dst[3] = make_float4(fx, fy, sbc, sba);
         }
+        a.binrec[idx] = brec;   // written for EVERY Gaussian; all zero = no tile
     }
 }
 

@@ -24,7 +24,7 @@ ABI_SYMBOLS = (
     "fdgs_forward", "fdgs_backward", "fdgs_mark_visible", "fdgs_debug_export_geom", "fdgs_debug_export_binning",
     "fdgs_profile_enable", "fdgs_profile_read", "fdgs_launch_count", "fdgs_pack_rows", "fdgs_unpack_rows",
     "fdgs_sh_outer_sum", "fdgs_check_rows_zero", "fdgs_l1_ssim_forward", "fdgs_l1_ssim_backward", "fdgs_adam_step",
-    "fdgs_knn_scratch_bytes", "fdgs_knn", "fdgs_debug_activate", "fdgs_union_maps",
+    "fdgs_knn_scratch_bytes", "fdgs_knn", "fdgs_debug_activate", "fdgs_union_maps", "fdgs_set_tile_cull",
 )
 
 STAGE_NAMES = ("preprocess_fwd", "bin_count_scan", "bin_scatter", "tile_sort_pack", "reserved", "blend_fwd", "blend_bwd",
@@ -79,6 +79,27 @@ def profile_read():
     calls = (ctypes.c_longlong * len(STAGE_NAMES))()
     lib().fdgs_profile_read(ms, calls)
     return {n: (ms[i], calls[i]) for i, n in enumerate(STAGE_NAMES)}
+
+
+def set_tile_cull(mode) -> int:
+    """1 (default): tile lists hold only the instances a pixel can blend; 0: the reference's lists exactly
+    (include/fdgs.h: fdgs_set_tile_cull).  Returns the previous mode."""
+    return int(lib().fdgs_set_tile_cull(1 if mode else 0))
+
+
+class tile_cull:
+    """Context manager: `with fdgs.tile_cull(0): ...` renders with the reference's tile lists."""
+
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = set_tile_cull(self.mode)
+        return self
+
+    def __exit__(self, *exc):
+        set_tile_cull(self.prev)
+        return False
 
 
 def launch_count():

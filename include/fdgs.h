@@ -317,6 +317,17 @@ int fdgs_debug_export_binning(const char* binning_buffer, const char* image_buff
 int fdgs_debug_activate(int n, const float* log_s, const float* logit, const float* quat, int mode, float* s_out,
                         float* o_out, float* q_out, void* stream);
 
+/* Tile lists.  The reference lists a Gaussian in every tile of the square of half-width ceil(3 sigma_max) around its
+ * centre (auxiliary.h:46-59 getRect, rasterizer_impl.cu:71-112), although only the pixels where
+ * alpha = min(0.99, opacity * exp(power)) reaches 1/255 ever blend it (forward.cu:590).
+ *   mode 1 (default): a Gaussian is listed only in the tiles that ellipse can reach (exact conservative test per tile).
+ *                     The instances dropped are instances no pixel would have blended: the images, radii, every other
+ *                     output and every gradient are unchanged; the PRIVATE scratch state differs from the
+ *                     reference's (shorter tile lists, smaller num_rendered, n_contrib counted in the shorter lists).
+ *   mode 0:           the reference's tile lists exactly (point_list, ranges, num_rendered, n_contrib bit-identical).
+ * Process-wide; returns the previous mode.  The environment variable FDGS_TILE_CULL sets the initial mode. */
+int fdgs_set_tile_cull(int mode);
+
 /* Measurement hooks (bench.py): per-stage device time with CUDA events recorded on the launch
  * stream, and a count of the kernels this library launched.  The reference has no equivalent
  * (it times whole iterations from Python, train.py:57-58,89,185). */

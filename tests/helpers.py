@@ -159,3 +159,47 @@ def golden(name):
 
 def to_np(t):
     return t.detach().cpu().numpy()
+
+
+def check_tile_lists(ours, ref, W, H, mode):
+    """Compare the private tile lists with the reference's.  ours / ref: dicts of numpy arrays
+    point_list [R], ranges [tiles, 2], n_contrib [H*W] (and num_rendered).
+
+    mode 0 (fdgs_set_tile_cull(0)): bit-identical.
+    mode 1 (default): every tile's list is the reference's list with some instances REMOVED (same order), and every
+    pixel's last contributor is the same Gaussian -- n_contrib itself counts positions of the shorter list.  That the
+    removed instances blend nowhere is what the bit-identical images of the same tests prove."""
+    op, orr, on = (np.asarray(ours[k]) for k in ("point_list", "ranges", "n_contrib"))
+    rp, rr, rn = (np.asarray(ref[k]) for k in ("point_list", "ranges", "n_contrib"))
+    orr, rr = orr.reshape(-1, 2).astype(np.int64), rr.reshape(-1, 2).astype(np.int64)
+    on, rn = on.reshape(-1).astype(np.int64), rn.reshape(-1).astype(np.int64)
+    if mode == 0:
+        assert int(ours["num_rendered"]) == int(ref["num_rendered"])
+        assert bitdiff(op, rp) == 0 and bitdiff(orr, rr) == 0 and bitdiff(on, rn) == 0
+        return
+    assert int(ours["num_rendered"]) <= int(ref["num_rendered"])
+    assert orr.shape == rr.shape
+    T = orr.shape[0]
+    olen, rlen = orr[:, 1] - orr[:, 0], rr[:, 1] - rr[:, 0]
+    assert int(olen.sum()) == int(ours["num_rendered"]) == len(op)
+    assert (olen <= rlen).all()
+    # (tile, gaussian) keys in list order; ours must equal the reference's filtered to the keys ours holds
+    otile = np.repeat(np.arange(T, dtype=np.int64), olen)
+    rtile = np.repeat(np.arange(T, dtype=np.int64), rlen)
+    # lists are stored tile after tile in both implementations; rebuild that order explicitly from the ranges
+    oidx = np.concatenate([np.arange(a, b) for a, b in orr if b > a]) if len(op) else np.zeros(0, np.int64)
+    ridx = np.concatenate([np.arange(a, b) for a, b in rr if b > a]) if len(rp) else np.zeros(0, np.int64)
+    okey = (otile << 32) | op[oidx].astype(np.int64)
+    rkey = (rtile << 32) | rp[ridx].astype(np.int64)
+    keep = np.isin(rkey, okey)
+    assert int(keep.sum()) == len(okey), "our lists hold an instance the reference's do not"
+    assert (rkey[keep] == okey).all(), "order inside a tile differs from the reference"
+    # last contributor of every pixel: the same Gaussian
+    gx = (W + 15) // 16
+    ys, xs = np.divmod(np.arange(W * H, dtype=np.int64), W)
+    tile = (ys // 16) * gx + xs // 16
+    assert ((on > 0) == (rn > 0)).all()
+    nz = on > 0
+    g_ours = op[orr[tile[nz], 0] + on[nz] - 1]
+    g_ref = rp[rr[tile[nz], 0] + rn[nz] - 1]
+    assert (g_ours == g_ref).all(), "a pixel's last contributor differs"

@@ -64,15 +64,20 @@ def check_grad_vs_reference(gname, a, runs):
         return
     l2 = ((a.double() - m).norm() / nm).item()
     err = (a.double() - m).abs().max().item() / sc
-    if l2n < 2e-4:
+    chain = gname in ("dL_dts", "dL_dscales", "dL_dscales_t", "dL_drot", "dL_drot_r", "dL_dcov3D")
+    if l2n < 2e-4 and not (chain and l2n > 1e-5):
         assert l2 < max(1e-4, 4 * l2n), (gname, "l2", l2, "ref spread", l2n)
         assert err < max(1e-4, 5 * mxn), (gname, "max", err, "ref spread", mxn)
     else:
+        # (Covariance-chain tensors whose reference spread is already above 1e-5 take this branch too: their norm
+        # error is a heavy-tailed statistic -- for ONE configuration and code version, three of our runs and three
+        # estimates of the reference's spread from 8 reruns each scattered over 4.3e-5 ... 7.3e-5 and 4.1e-5 ... 5.4e-5
+        # on dL_dts, profiles/r02_grad_noise_probe.txt -- so the norm gets 6 spreads and the rows carry the check.)
         # The reference does not reproduce ITSELF to 0.02 % here (cfg5's long time axis: a handful of Gaussians with
         # near-singular conditional covariances carry most of the norm and amplify the atomics' rounding noise to
         # 5-30 %, profiles/r02_parity_table.md).  Norms are then heavy-tailed statistics of a few rows: keep a loose
         # norm bound and check the well-conditioned majority row by row instead.
-        assert l2 < 6 * l2n, (gname, "l2", l2, "ref spread", l2n)
+        assert l2 < max(1e-4, 6 * l2n), (gname, "l2", l2, "ref spread", l2n)
 
         def median_row_err(x):
             d = (x.double() - m).reshape(m.shape[0], -1).norm(dim=1)
@@ -82,6 +87,21 @@ def check_grad_vs_reference(gname, a, runs):
         ours_med = median_row_err(a)
         ref_med = max(median_row_err(r) for r in runs)
         assert ours_med < max(1e-4, 3 * ref_med), (gname, "median row error", ours_med, "reference runs", ref_med)
+
+
+@pytest.fixture(params=[1, 0], ids=["tilecull", "reflists"])
+def tile_mode(request):
+    """1 = the library's default tile lists (only instances a pixel can blend), 0 = the reference's lists exactly
+    (include/fdgs.h: fdgs_set_tile_cull)."""
+    import fdgs
+    prev = fdgs.set_tile_cull(request.param)
+    yield request.param
+    fdgs.set_tile_cull(prev)
+
+
+def lists_of(o):
+    return dict(point_list=helpers.to_np(o["point_list"]), ranges=helpers.to_np(o["ranges"]),
+                n_contrib=helpers.to_np(o["n_contrib"]).reshape(-1), num_rendered=int(o["fw"][0]))
 
 
 def run_cuda(C, name_or_cfg, with_backward=True, grads=None):
@@ -113,18 +133,16 @@ GOLDEN_CASES = ["tiny", "small", "flowbg", "negfov", "ragged", "sh3d", "dim3", "
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
-def test_forward_bit_exact_vs_golden(C, name):
+def test_forward_bit_exact_vs_golden(C, name, tile_mode):
     G = helpers.golden(name)
     if G is None:
         pytest.skip("no golden fixture for %s" % name)
     o = run_cuda(C, name, with_backward=False)
     fw = o["fw"]
     np_ = helpers.to_np
-    assert fw[0] == int(G["num_rendered"])
     assert helpers.bitdiff(np_(fw[5]), G["radii"]) == 0
-    assert helpers.bitdiff(np_(o["point_list"]), G["point_list"]) == 0
-    assert helpers.bitdiff(np_(o["ranges"]), G["ranges"]) == 0
-    assert helpers.bitdiff(np_(o["n_contrib"]).reshape(-1), G["n_contrib"]) == 0
+    helpers.check_tile_lists(lists_of(o), dict(point_list=G["point_list"], ranges=G["ranges"], n_contrib=G["n_contrib"],
+                                               num_rendered=int(G["num_rendered"])), o["cfg"]["W"], o["cfg"]["H"], tile_mode)
     vis = G["radii"] > 0
     assert helpers.bitdiff(np_(o["tiles"]), G["tiles_touched"]) == 0
     assert helpers.bitdiff(np_(fw[10]), G["out_means3D"]) == 0
@@ -183,7 +201,7 @@ def test_colour_only_backward_equals_zero_aux_gradients(C, name):
 
 
 @pytest.mark.parametrize("P,expect_min", [(4000, 0), (30000, 2049), (200000, 16385)])
-def test_tile_lists_sorted_and_complete(C, P, expect_min):
+def test_tile_lists_sorted_and_complete(C, P, expect_min, tile_mode):
     """Every path of the per-tile sort (<= 2048 keys: 8 keys per thread; <= 16384: the large
     shared-memory instantiation; above: in place in global memory) must produce, for every tile,
     exactly the instances whose tile rectangle covers it, ordered by (depth bits, Gaussian index) --
@@ -196,6 +214,7 @@ def test_tile_lists_sorted_and_complete(C, P, expect_min):
     depth_bits = helpers.to_np(o["depths"]).astype(np.float32).view(np.uint32).astype(np.uint64)
     ranges = helpers.to_np(o["ranges"]).reshape(-1, 2).astype(np.int64)
     plist = helpers.to_np(o["point_list"]).astype(np.int64)
+    con = helpers.to_np(o["conic_opacity"])
     gx = gy = 2
     r = radii.astype(np.float32)
     f = np.float32
@@ -204,7 +223,8 @@ def test_tile_lists_sorted_and_complete(C, P, expect_min):
     x1 = np.clip(((((px + r) + f(16.0)) + f(-1.0)) * f(0.0625)).astype(np.int64), 0, gx)
     y1 = np.clip(((((py + r) + f(16.0)) + f(-1.0)) * f(0.0625)).astype(np.int64), 0, gy)
     vis = radii > 0
-    assert (ranges[:, 1] - ranges[:, 0]).max() >= expect_min, "configuration does not reach the intended sort path"
+    if tile_mode == 0:
+        assert (ranges[:, 1] - ranges[:, 0]).max() >= expect_min, "configuration does not reach the intended sort path"
     assert (ranges[:, 1] - ranges[:, 0]).sum() == int(o["fw"][0]) == len(plist)
     for ty in range(gy):
         for tx in range(gx):
@@ -213,15 +233,36 @@ def test_tile_lists_sorted_and_complete(C, P, expect_min):
             want = np.nonzero(vis & (x0 <= tx) & (tx < x1) & (y0 <= ty) & (ty < y1))[0]
             key = (depth_bits[want] << np.uint64(32)) | want.astype(np.uint64)
             want = want[np.argsort(key, kind="stable")]
-            assert len(ids) == len(want)
-            assert (ids == want).all()
+            if tile_mode == 0:
+                assert len(ids) == len(want)
+                assert (ids == want).all()
+                continue
+            # default lists: the reference's list with instances removed, order kept ...
+            keep = np.isin(want, ids)
+            assert int(keep.sum()) == len(ids) and (want[keep] == ids).all()
+            # ... and no pixel of the tile reaches alpha = 1/255 for a removed instance (float64, 1 % margin; the cull
+            # keeps 2 % of slack)
+            gone = want[~keep]
+            xs = (np.arange(16) + 16 * tx).astype(np.float64)
+            ys = (np.arange(16) + 16 * ty).astype(np.float64)
+            for lo_g in range(0, len(gone), 20000):
+                gsel = gone[lo_g:lo_g + 20000]
+                cx, cy = px[gsel].astype(np.float64), py[gsel].astype(np.float64)
+                A, B, Cc, op_ = (con[gsel, i].astype(np.float64) for i in range(4))
+                dx = cx[:, None, None] - xs[None, None, :]
+                dy = cy[:, None, None] - ys[None, :, None]
+                power = -0.5 * (A[:, None, None] * dx * dx + Cc[:, None, None] * dy * dy) - B[:, None, None] * dx * dy
+                alpha = op_[:, None, None] * np.exp(np.minimum(power, 0.0))
+                assert not ((power <= 0) & (alpha >= (1.0 / 255.0) * 0.99)).any(), "a removed instance had a contributing pixel"
+    if tile_mode == 1 and P >= 30000:
+        assert int(o["fw"][0]) < (x1 - x0)[vis].dot((y1 - y0)[vis]), "tile culling removed nothing"
 
 
 # ---------------------------------------------------------------------------------------------------
 # 2. the compiled reference at BASELINE sizes
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["mid", "mid_rotcam", "mid_dur10", "mid_smod2", "cfg5", "cfg2", "cfg3"])
-def test_full_size_vs_compiled_reference(C, name):
+def test_full_size_vs_compiled_reference(C, name, tile_mode):
     if not oracle_py.ref_available():
         pytest.skip("oracle/_ref/ref_rasterizer.so not present")
     ref = oracle_py.ref_module()
@@ -233,11 +274,13 @@ def test_full_size_vs_compiled_reference(C, name):
     rb = reruns[0]
     torch.cuda.synchronize()
     eq = lambda a, b: bool(torch.equal(a.contiguous().view(torch.int32), b.contiguous().view(torch.int32)))
-    assert fw[0] == rf[0]
     assert eq(fw[5], rf[5])                                                  # radii
-    assert eq(o["point_list"], oracle_py.ref_binning_point_list(rf[7], rf[0]))   # tile assignment + order
     ri = oracle_py.ref_image_views(rf[8], W * H)
-    assert eq(o["n_contrib"].view(-1), ri["n_contrib"])
+    n_tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    # tile assignment + order, last contributors (bit-identical lists in reference-list mode)
+    helpers.check_tile_lists(lists_of(o), dict(point_list=helpers.to_np(oracle_py.ref_binning_point_list(rf[7], rf[0])),
+                                               ranges=helpers.to_np(ri["ranges"][:n_tiles]), n_contrib=helpers.to_np(ri["n_contrib"]),
+                                               num_rendered=int(rf[0])), W, H, tile_mode)
     for i in (1, 2, 3, 4, 10):                                               # color, flow, depth, T, out_means3D
         assert eq(fw[i], rf[i]), i
     vis = rf[5] > 0
@@ -283,17 +326,20 @@ ORACLE_CASES = ["tiny", "flowbg", "negfov", "ragged", "sh3d", "dim3", "norot4d",
 
 
 @pytest.mark.parametrize("name", ORACLE_CASES)
-def test_vs_cpu_oracle(C, name):
+def test_vs_cpu_oracle(C, name, tile_mode):
     o = run_cuda(C, name)
     cfg, fw = o["cfg"], o["fw"]
     cfg_c, cam, sc_c, st_c = helpers.build(name)
     inp = helpers.oracle_inputs(st_c, sc_c, cfg_c)
     f = oracle_py.forward(inp)
     np_ = helpers.to_np
-    assert fw[0] == f["num_rendered"]
     assert helpers.bitdiff(np_(fw[5]), f["radii"]) == 0
-    assert helpers.bitdiff(np_(o["point_list"]), f["point_list"]) == 0
-    assert helpers.bitdiff(np_(o["ranges"]), f["ranges"]) == 0
+    if tile_mode == 0:
+        assert fw[0] == f["num_rendered"]
+        assert helpers.bitdiff(np_(o["point_list"]), f["point_list"]) == 0
+        assert helpers.bitdiff(np_(o["ranges"]), f["ranges"]) == 0
+    else:
+        assert fw[0] <= f["num_rendered"]      # the shorter lists are compared with the reference's in the tests above
     vis = f["radii"] > 0
     assert helpers.bitdiff(np_(fw[10]), f["out_means3D"]) == 0
     for ours, key in ((o["depths"], "depths"), (o["means2D"], "means2D"), (o["rgb"], "rgb"), (fw[9], "cov3D")):
@@ -301,7 +347,8 @@ def test_vs_cpu_oracle(C, name):
     assert helpers.bitdiff(np_(o["conic_opacity"])[vis][:, :3], f["conic_opacity"][vis][:, :3]) == 0
     assert helpers.max_rel(np_(o["conic_opacity"])[vis][:, 3], f["conic_opacity"][vis][:, 3]) < 1e-6   # MUFU vs libm
     # n_contrib can only differ where CUDA's expf and libm's land on opposite sides of a blend threshold
-    assert helpers.bitdiff(np_(o["n_contrib"]), f["n_contrib"]) <= max(2, cfg["W"] * cfg["H"] // 20000)
+    if tile_mode == 0:
+        assert helpers.bitdiff(np_(o["n_contrib"]), f["n_contrib"]) <= max(2, cfg["W"] * cfg["H"] // 20000)
     for idx, key in ((1, "color"), (2, "flow"), (3, "depth")):
         assert helpers.max_rel(np_(fw[idx]), f[key]) < 1e-5, key
     assert helpers.psnr(np_(fw[1]), f["color"]) > 100
@@ -388,7 +435,16 @@ def test_full_size_properties(C):
     cfg, fw = o["cfg"], o["fw"]
     R = fw[0]
     P, W, H = cfg["P"], cfg["W"], cfg["H"]
-    assert R == int(o["tiles"].long().sum())
+    # the lists hold only instances a pixel can blend (fdgs_set_tile_cull, default): never more than the reference's
+    # tile rectangles (tiles_touched keeps the reference's count), and far fewer on this scene
+    assert R <= int(o["tiles"].long().sum())
+    import fdgs
+    with fdgs.tile_cull(0):
+        fw_ref_lists = C.rasterize_gaussians(*helpers.fwd_args(o["st"], o["sc"], cfg))
+    assert fw_ref_lists[0] == int(o["tiles"].long().sum())
+    for i in (1, 2, 3, 4, 5, 10):     # colour, flow, depth, T, radii, out_means3D: independent of the list mode
+        assert torch.equal(fw[i], fw_ref_lists[i]), i
+    del fw_ref_lists
     ranges = o["ranges"].long()
     pl = o["point_list"].long()
     # ranges tile the instance list exactly
