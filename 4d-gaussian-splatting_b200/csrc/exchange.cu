@@ -91,6 +91,27 @@ __global__ void __launch_bounds__(256) union_maps_kernel(long long P, const int*
 
 }  // namespace
 
+// Per-view densification statistics in one pass (reference: train.py:164-183, scene/gaussian_model.py:579-589):
+//   grad_norm_sum[i] += ||viewspace_grad[i, :2]||,  visibility_count[i] += (radii[i] > 0),  max_radii[i] = max(., radii[i])
+static __global__ void __launch_bounds__(256) view_stats_kernel(long long P, const float* __restrict__ vgrad, int vstride,
+                                                         const int* __restrict__ radii, float* __restrict__ grad_norm_sum,
+                                                         float* __restrict__ visibility_count, int* __restrict__ max_radii) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float gx = vgrad[i * vstride + 0], gy = vgrad[i * vstride + 1];
+    const int r = radii[i];
+    grad_norm_sum[i] += sqrtf(gx * gx + gy * gy);
+    if (r > 0) visibility_count[i] += 1.0f;
+    if (r > max_radii[i]) max_radii[i] = r;
+}
+
+cudaError_t launch_view_stats(long long P, const float* vgrad, int vstride, const int* radii, float* grad_norm_sum,
+                              float* visibility_count, int* max_radii, cudaStream_t stream) {
+    if (P <= 0) return cudaSuccess;
+    view_stats_kernel<<<(unsigned)((P + 255) / 256), 256, 0, stream>>>(P, vgrad, vstride, radii, grad_norm_sum, visibility_count, max_radii);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_union_maps(long long P, const int* radii, const int* cs, int* slot_of, long long* idx, cudaStream_t stream) {
     if (P <= 0) return cudaSuccess;
     union_maps_kernel<<<(unsigned)((P + 255) / 256), 256, 0, stream>>>(P, radii, cs, slot_of, idx);

@@ -472,6 +472,18 @@ int fdgs_union_maps(long long P, const int* radii, const int* cs, int* slot_of, 
     return FDGS_OK;
 }
 
+int fdgs_view_stats(long long P, const float* viewspace_grad, int grad_stride, const int* radii, float* grad_norm_sum,
+                    float* visibility_count, int* max_radii, void* stream_v) {
+    g_last_error.clear();
+    if (P < 0 || grad_stride < 2) return fail(FDGS_ERR_INVALID_ARG, "bad P / gradient row stride");
+    if (P == 0) return FDGS_OK;
+    if (!viewspace_grad || !radii || !grad_norm_sum || !visibility_count || !max_radii) return fail(FDGS_ERR_INVALID_ARG, "null argument");
+    FDGS_CUDA(fdgs::launch_view_stats(P, viewspace_grad, grad_stride, radii, grad_norm_sum, visibility_count, max_radii,
+                                      reinterpret_cast<cudaStream_t>(stream_v)), "view_stats");
+    g_kernel_launches += 1;
+    return FDGS_OK;
+}
+
 int fdgs_check_rows_zero(int n, const float* const* tensors, const int* widths, long long P, const int* radii, int* flag,
                          void* stream_v) {
     g_last_error.clear();

@@ -207,6 +207,8 @@ cudaError_t launch_rows_zero_check(int n, const float* const* tensors, const int
                                    int* flag, cudaStream_t stream);
 
 cudaError_t launch_union_maps(long long P, const int* radii, const int* cs, int* slot_of, long long* idx, cudaStream_t stream);
+cudaError_t launch_view_stats(long long P, const float* vgrad, int vstride, const int* radii, float* grad_norm_sum,
+                              float* visibility_count, int* max_radii, cudaStream_t stream);
 cudaError_t launch_pack_rows(bool unpack, int n, float* const* tensors, const int* widths, const long long* block_off,
                              const long long* idx, long long K, float* flat, cudaStream_t stream);
 

@@ -469,68 +469,78 @@ __device__ __forceinline__ void store_sh_row(const ShSumParams& a, size_t idx, c
     }
 }
 
-// Phase B.  Blocks [0, union_blocks): 4 threads per UNION Gaussian (dense warps: the list a.union_idx), thread kg owns
-// the coefficients 4 kg .. 4 kg + 3 of each of the three 16-blocks and sums the V rank-one rows into registers; the 32
-// rows of a block are staged in shared memory and stored warp-per-row, fully coalesced.
+// Phase B.  Blocks [0, union_blocks): 32 UNION Gaussians per block (dense: the list a.union_idx), one per lane; warp kg
+// owns the coefficients 4 kg .. 4 kg + 3 of each of the three 16-blocks (warp-uniform, so only those four basis
+// functions are evaluated) and sums the V rank-one rows into registers; the 32 rows of a block are staged in shared
+// memory and stored warp-per-row, fully coalesced.
 // Blocks beyond: the rows of all other Gaussians are zero-filled, warp per row.
 constexpr int SO_ROWS = 32;          // union Gaussians per block (128 threads)
 constexpr int SO_STRIDE = 148;       // floats per staged row (144 + padding: conflict-free float4 stores)
+
+template <int KG>
+__device__ __forceinline__ void sh_outer_accumulate(const ShSumParams& a, int k, float (&acc)[3][12]) {
+    const bool sh4d = !((a.gaussian_dim == 3) || a.force_sh_3d);
+    const int ncoef = (a.D + 1) * (a.D + 1);
+    const int nblk = (sh4d && a.D > 2 && a.D_t > 0) ? ((a.D_t > 1) ? 3 : 2) : 1;
+    for (int v = 0; v < a.V; ++v) {
+        const float4* src = reinterpret_cast<const float4*>(a.dirs) + 2 * ((size_t)v * a.K + k);
+        const float4 d0 = src[0], d1 = src[1];
+        if (d1.x == 0.f && d1.y == 0.f && d1.z == 0.f) continue;   // not rendered by view v
+        const float tw1 = d0.w, tw2 = d1.w;
+        ShDeriv S;
+        sh_basis_deriv(d0.x, d0.y, d0.z, a.D, S);   // only l[4 KG .. 4 KG + 3] (and l[0]) survive dead-code elimination
+        const float drgb[3] = {d1.x, d1.y, d1.z};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k2 = 4 * KG + j;
+            if (k2 >= ncoef) continue;
+            const float lk = S.l[k2];
+            const float w0 = (sh4d && k2 == 1) ? S.l[0] : lk;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                acc[0][3 * j + ch] = __fadd_rn(acc[0][3 * j + ch], __fmul_rn(w0, drgb[ch]));
+                if (nblk > 1) acc[1][3 * j + ch] = __fadd_rn(acc[1][3 * j + ch], __fmul_rn(__fmul_rn(tw1, lk), drgb[ch]));
+                if (nblk > 2) acc[2][3 * j + ch] = __fadd_rn(acc[2][3 * j + ch], __fmul_rn(__fmul_rn(tw2, lk), drgb[ch]));
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128) sh_outer_sum_kernel(const ShSumParams a, const int union_blocks) {
     __shared__ __align__(16) float rowbuf[SO_ROWS][SO_STRIDE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if ((int)blockIdx.x >= union_blocks) {
-        // zero rows: this block covers 128 consecutive Gaussians, a warp per row
-        const long long base = (long long)(blockIdx.x - union_blocks) * 128;
-        for (int r = warp; r < 128; r += 4) {
-            const long long idx = base + r;
-            if (idx >= a.P) break;
-            if (a.slot_of[idx] >= 0 || a.accumulate) continue;
-            store_sh_row(a, (size_t)idx, nullptr, lane);
+        // zero rows: this block covers 128 consecutive Gaussians, 32 per warp; the warp reads their 32 union slots with
+        // one coalesced load, then zero-fills the rows that are not in the union (no dependent load per row)
+        if (a.accumulate) return;
+        const long long base = (long long)(blockIdx.x - union_blocks) * 128 + 32 * warp;
+        const long long mine = base + lane;
+        unsigned todo = __ballot_sync(0xffffffffu, mine < a.P && a.slot_of[mine] < 0);
+        while (todo) {
+            const int r = __ffs(todo) - 1;
+            todo &= todo - 1;
+            store_sh_row(a, (size_t)(base + r), nullptr, lane);
         }
         return;
     }
-    const int k = blockIdx.x * SO_ROWS + (threadIdx.x >> 2);
-    const int kg = threadIdx.x & 3;
+    const int k = blockIdx.x * SO_ROWS + lane;
+    const int kg = warp;
     float acc[3][12];
 #pragma unroll
     for (int b = 0; b < 3; ++b)
 #pragma unroll
         for (int i = 0; i < 12; ++i) acc[b][i] = 0.f;
+    long long my_idx = -1;
     if (k < a.K) {
-        const bool sh4d = !((a.gaussian_dim == 3) || a.force_sh_3d);
-        const int ncoef = (a.D + 1) * (a.D + 1);
-        const int nblk = (sh4d && a.D > 2 && a.D_t > 0) ? ((a.D_t > 1) ? 3 : 2) : 1;
-        for (int v = 0; v < a.V; ++v) {
-            const float4* src = reinterpret_cast<const float4*>(a.dirs) + 2 * ((size_t)v * a.K + k);
-            const float4 d0 = src[0], d1 = src[1];
-            if (d1.x == 0.f && d1.y == 0.f && d1.z == 0.f) continue;   // not rendered by view v
-            float gx = d0.x, gy = d0.y, gz = d0.z;
-            const float tw1 = d0.w, tw2 = d1.w;
-            ShDeriv S;
-            sh_basis_deriv(gx, gy, gz, a.D, S);
-            const float drgb[3] = {d1.x, d1.y, d1.z};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {   // select l[4 kg + j] without dynamic register indexing
-                    if (q != kg) continue;
-                    const int k2 = 4 * q + j;
-                    if (k2 >= ncoef) continue;
-                    const float lk = S.l[k2];
-                    const float w0 = (sh4d && k2 == 1) ? S.l[0] : lk;
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
-                        acc[0][3 * j + ch] = __fadd_rn(acc[0][3 * j + ch], __fmul_rn(w0, drgb[ch]));
-                        if (nblk > 1) acc[1][3 * j + ch] = __fadd_rn(acc[1][3 * j + ch], __fmul_rn(__fmul_rn(tw1, lk), drgb[ch]));
-                        if (nblk > 2) acc[2][3 * j + ch] = __fadd_rn(acc[2][3 * j + ch], __fmul_rn(__fmul_rn(tw2, lk), drgb[ch]));
-                    }
-                }
-            }
-        }
+        if (kg == 0) sh_outer_accumulate<0>(a, k, acc);
+        else if (kg == 1) sh_outer_accumulate<1>(a, k, acc);
+        else if (kg == 2) sh_outer_accumulate<2>(a, k, acc);
+        else sh_outer_accumulate<3>(a, k, acc);
+        my_idx = a.union_idx[k];     // the destination row of lane `lane`'s Gaussian (shuffled to the storing warp below)
     }
     // stage: coefficients 16 b + 4 kg + j of the row -> floats 48 b + 12 kg + 3 j + ch
     {
-        float* dst = &rowbuf[threadIdx.x >> 2][0];
+        float* dst = &rowbuf[lane][0];
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
             float4* q = reinterpret_cast<float4*>(dst + 48 * b + 12 * kg);
@@ -541,9 +551,9 @@ __global__ void __launch_bounds__(128) sh_outer_sum_kernel(const ShSumParams a, 
     }
     __syncthreads();
     for (int r = warp; r < SO_ROWS; r += 4) {
-        const int kr = blockIdx.x * SO_ROWS + r;
-        if (kr >= a.K) break;
-        store_sh_row(a, (size_t)a.union_idx[kr], &rowbuf[r][0], lane);
+        const long long dst_row = __shfl_sync(0xffffffffu, my_idx, r);
+        if (dst_row < 0) break;     // rows beyond K (only in the last block; warp-uniform)
+        store_sh_row(a, (size_t)dst_row, &rowbuf[r][0], lane);
     }
 }
 

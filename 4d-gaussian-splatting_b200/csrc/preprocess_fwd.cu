@@ -24,6 +24,17 @@ namespace {
 constexpr int PRE_THREADS = 128;
 constexpr int PRE_CAP = 48;       // shared-memory SH row slots per CTA (rendered rows per round)
 
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 struct ShBasis {
     float l[16];   // l0m0, l1m1, l1m0, l1p1, l2m2 .. l3p3
 };
@@ -436,11 +447,16 @@ __global__ void __launch_bounds__(PRE_THREADS, 5) preprocess_fwd_kernel(const Pr
             if (a.tile_cull) {
                 if (pmin == INFINITY) {
                     tx1 = tx0; ty1 = ty0;
-                } else if (pmin > -3.0e38f) {
+                } else if (pmin > -3.0e38f && cdet > 2.0e-3f * conx * conz) {
+                    // (Very thin Gaussians -- axis ratio above ~2000, det < 2e-3 A C -- keep the reference's rectangle: far
+                    // from their centre the terms of q are thousands of times larger than q itself, and the blend loop's
+                    // own fp32 rounding of `power` can then exceed the 0.02 slack of the cut.)
                     // bounding box of { d : 0.5 d^T Q d <= -pmin }: half extents sqrt(2 q C / det), sqrt(2 q A / det)
+                    // (approximate reciprocal / square root, 1-2 ulp: far inside the margins below)
                     const float q2 = -2.f * pmin;
-                    const float ex = sqrtf(q2 * conz / cdet) * 1.0001f + 0.01f;
-                    const float ey = sqrtf(q2 * conx / cdet) * 1.0001f + 0.01f;
+                    const float q2_det = q2 * rcp_approx(cdet);
+                    const float ex = sqrt_approx(q2_det * conz) * 1.0001f + 0.01f;
+                    const float ey = sqrt_approx(q2_det * conx) * 1.0001f + 0.01f;
                     if (ex <= 1.0e6f && ey <= 1.0e6f && fabsf(px) <= 1.0e6f && fabsf(py) <= 1.0e6f) {
                         // pixel centres are the integers: pixel p lies in tile floor(p / 16)
                         tx0 = max(rx0, (int)floorf((px - ex) * (1.0f / TILE_X)));
@@ -449,15 +465,39 @@ __global__ void __launch_bounds__(PRE_THREADS, 5) preprocess_fwd_kernel(const Pr
                         ty1 = min(ry1, (int)floorf((py + ey) * (1.0f / TILE_Y)) + 1);
                         if (tx1 <= tx0 || ty1 <= ty0) { tx1 = tx0; ty1 = ty0; }
                         const int tw = tx1 - tx0, tn = tw * (ty1 - ty0);
-                        if (tn > 0 && tn <= 32) {
+                        // Per tile row, the x-interval [L, U] of the ellipse inside the row's y-band (the ellipse cut by
+                        // a band is convex: its x-extent peaks at dy* = -(B/C) dx, so when dy* lies outside the band the
+                        // extent is reached on the band edge nearest to it: a root of A dx^2 + 2 B dy dx + C dy^2 = 2 q).
+                        // A tile takes an instance iff its columns meet [L, U] -- in exact arithmetic the same decision as
+                        // minimising q over the tile; margins of 1e-3 |x| + 0.01 px cover the rounding.
+                        if (tn > 0 && tn <= 32 && (tx1 - tx0) > 1 && (ty1 - ty0) > 1) {
                             tmask = 0u;
-                            int cx = tx0, cy = ty0;
-                            for (int i = 0; i < tn; ++i) {
-                                const float bx0 = (float)(cx * TILE_X), by0 = (float)(cy * TILE_Y);
-                                if (rect_may_contribute(px, py, conx, cony, conz, pmin, sbc, sba, bx0, bx0 + (float)(TILE_X - 1), by0,
-                                                        by0 + (float)(TILE_Y - 1)))
-                                    tmask |= 1u << i;
-                                if (++cx == tx1) { cx = tx0; ++cy; }
+                            const float inv_a = rcp_approx(conx);
+                            const float dy_hi = sbc * ex, dy_lo = -dy_hi;     // dy of the right-most / left-most ellipse point
+                            int bit0 = 0;
+                            for (int cy = ty0; cy < ty1; ++cy, bit0 += tw) {
+                                const float a0 = (float)(cy * TILE_Y) - py, b0 = a0 + (float)(TILE_Y - 1);
+                                float U = ex, L = -ex;
+                                bool hit = true;
+                                if (!(dy_hi >= a0 && dy_hi <= b0)) {
+                                    const float dyc = fminf(fmaxf(dy_hi, a0), b0);
+                                    const float disc = q2 * conx - cdet * dyc * dyc;
+                                    hit = disc >= -1.0e-3f * q2 * conx;
+                                    U = (-cony * dyc + sqrt_approx(fmaxf(disc, 0.f))) * inv_a;
+                                }
+                                if (hit && !(dy_lo >= a0 && dy_lo <= b0)) {
+                                    const float dyc = fminf(fmaxf(dy_lo, a0), b0);
+                                    const float disc = q2 * conx - cdet * dyc * dyc;
+                                    hit = disc >= -1.0e-3f * q2 * conx;
+                                    L = (-cony * dyc - sqrt_approx(fmaxf(disc, 0.f))) * inv_a;
+                                }
+                                if (!hit) continue;
+                                U += 1.0e-3f * fabsf(U) + 0.01f;
+                                L -= 1.0e-3f * fabsf(L) + 0.01f;
+                                const int c0 = max(tx0, (int)floorf((px + L) * (1.0f / TILE_X)));
+                                const int c1 = min(tx1 - 1, (int)floorf((px + U) * (1.0f / TILE_X)));
+                                if (c1 >= c0)
+                                    tmask |= (uint32_t)(((1ull << (c1 - c0 + 1)) - 1ull) << (bit0 + c0 - tx0));
                             }
                             if (tmask == 0u) { tx1 = tx0; ty1 = ty0; }
                         }

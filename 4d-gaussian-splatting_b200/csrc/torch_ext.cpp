@@ -349,6 +349,23 @@ std::tuple<torch::Tensor, torch::Tensor> UnionMaps(const torch::Tensor& radii, c
     return std::make_tuple(slot_of, idx);
 }
 
+// per-view densification statistics, one pass (include/fdgs.h: fdgs_view_stats)
+void ViewStats(const torch::Tensor& viewspace_grad, const torch::Tensor& radii, torch::Tensor& grad_norm_sum,
+               torch::Tensor& visibility_count, torch::Tensor& max_radii) {
+    const long long P = radii.numel();
+    TORCH_CHECK(viewspace_grad.is_cuda() && viewspace_grad.scalar_type() == torch::kFloat32 && viewspace_grad.is_contiguous() &&
+                viewspace_grad.dim() == 2 && viewspace_grad.size(0) == P && viewspace_grad.size(1) >= 2, "fdgs: viewspace_grad must be [P,>=2] float32 CUDA");
+    TORCH_CHECK(radii.is_cuda() && radii.scalar_type() == torch::kInt32 && radii.is_contiguous(), "fdgs: radii must be int32 CUDA");
+    TORCH_CHECK(grad_norm_sum.is_contiguous() && grad_norm_sum.numel() == P && grad_norm_sum.scalar_type() == torch::kFloat32 &&
+                visibility_count.is_contiguous() && visibility_count.numel() == P && visibility_count.scalar_type() == torch::kFloat32 &&
+                max_radii.is_contiguous() && max_radii.numel() == P && max_radii.scalar_type() == torch::kInt32, "fdgs: statistics tensors");
+    const c10::cuda::CUDAGuard guard(radii.device());
+    cudaStream_t stream = c10::cuda::getCurrentCUDAStream().stream();
+    check(fdgs_view_stats(P, viewspace_grad.data_ptr<float>(), (int)viewspace_grad.size(1), radii.data_ptr<int>(),
+                          grad_norm_sum.data_ptr<float>(), visibility_count.data_ptr<float>(), max_radii.data_ptr<int>(), (void*)stream),
+          "view_stats");
+}
+
 // 1-element int32 tensor, non-zero if a row of `tensors` outside radii > 0 is not all-zero (sparse-exchange guard)
 torch::Tensor CheckRowsZero(std::vector<torch::Tensor> tensors, const torch::Tensor& radii) {
     TORCH_CHECK((int)tensors.size() <= FDGS_MAX_PACK, "fdgs: too many tensors");
@@ -589,6 +606,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("sh_outer_sum", &ShOuterSum);
     m.def("check_rows_zero", &CheckRowsZero);
     m.def("union_maps", &UnionMaps);
+    m.def("view_stats", &ViewStats);
     m.def("mark_visible", &markVisible);
     m.def("debug_export_geom", &DebugExportGeom);
     m.def("debug_export_binning", &DebugExportBinning);

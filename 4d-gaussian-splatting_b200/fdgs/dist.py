@@ -147,6 +147,11 @@ class ViewBatchStats:
         self.radii_reduced = False
 
     def add_view(self, viewspace_grad: torch.Tensor, radii: torch.Tensor):
+        if (viewspace_grad.is_cuda and viewspace_grad.dtype == torch.float32 and viewspace_grad.is_contiguous()
+                and radii.dtype == torch.int32 and radii.is_contiguous()):
+            import fdgs
+            fdgs.ext().view_stats(viewspace_grad, radii, self.grad_norm_sum, self.visibility_count, self.max_radii)
+            return
         self.grad_norm_sum += torch.norm(viewspace_grad[:, :2], dim=-1, keepdim=True)
         self.visibility_count += (radii > 0).to(self.visibility_count.dtype).view(-1, 1)
         self.max_radii = torch.max(self.max_radii, radii.to(torch.int32))

@@ -262,6 +262,12 @@ int fdgs_sh_outer_sum(const fdgs_sh_sum_args* args, void* stream);
 int fdgs_check_rows_zero(int n, const float* const* tensors, const int* widths, long long P, const int* radii,
                          int* flag, void* stream);
 
+/* Densification statistics of ONE view, accumulated in one pass (reference: train.py:164-183 -- viewspace gradient norm,
+ * visibility, max radius per Gaussian): grad_norm_sum[i] += ||viewspace_grad[i, 0:2]||, visibility_count[i] += radii[i] > 0,
+ * max_radii[i] = max(max_radii[i], radii[i]).  grad_stride = floats per row of viewspace_grad (3 for means2D.grad). */
+int fdgs_view_stats(long long P, const float* viewspace_grad, int grad_stride, const int* radii, float* grad_norm_sum,
+                    float* visibility_count, int* max_radii, void* stream);
+
 /* ---- the callers either side of the rasterizer in a training step ---------------------- */
 
 /* Fused photometric loss (reference: utils/loss_utils.py:18-64 l1_loss + ssim, combined as train.py:115-117):

@@ -387,7 +387,10 @@ def test_precomputed_colors_and_covariance_vs_oracle(C):
                                  cov3D_precomp=cov6)
     f = oracle_py.forward(inp)
     np_ = helpers.to_np
-    assert fw[0] == f["num_rendered"]
+    import fdgs
+    with fdgs.tile_cull(0):
+        assert C.rasterize_gaussians(*args)[0] == f["num_rendered"]     # the reference's tile lists
+    assert fw[0] <= f["num_rendered"]                                   # default lists: only instances a pixel can blend
     assert helpers.bitdiff(np_(fw[5]), f["radii"]) == 0
     assert helpers.max_rel(np_(fw[1]), f["color"]) < 1e-5
     grads = helpers.pixel_grads(cfg, device=DEV)

@@ -80,7 +80,7 @@ def _sequential(cfg, sc, cams, device, split_sh):
     return pc, stats
 
 
-def _view_parallel(cfg, sc, cams, view_ids, device, split_sh, group=None):
+def _view_parallel(cfg, sc, cams, view_ids, device, split_sh, group=None, views_per_rank=None):
     from gaussian_renderer import render
     from fdgs.dist import ViewParallelStep
     pc = _Model(sc, split_sh)
@@ -93,7 +93,7 @@ def _view_parallel(cfg, sc, cams, view_ids, device, split_sh, group=None):
             G = torch.randn(3, cfg["H"], cfg["W"], generator=g).to(device)
             ((pkg["render"] * G).sum() / len(cams)).backward()
             step.add_view_stats(pkg["viewspace_points"].grad, pkg["radii"])
-    stats = step.finish(pc.geometry(), pc.sh_leaves)
+    stats = step.finish(pc.geometry(), pc.sh_leaves, views_per_rank=views_per_rank)
     return pc, stats, step.info
 
 
@@ -102,11 +102,16 @@ def _cmp(pa, pb, sa, sb, tol_sh, tol_geo, tol_chain=None):
     rotations): both sides run the same non-deterministic blend backward, whose 1e-7 noise the chain amplifies (see
     test_gpu_parity.py) -- tol_chain, which grows with the scene size."""
     tol_chain = tol_geo if tol_chain is None else tol_chain
-    for a, b in zip(pa.sh_leaves, pb.sh_leaves):
+    for j, (a, b) in enumerate(zip(pa.sh_leaves, pb.sh_leaves)):
         assert a.grad is not None and b.grad is not None
-        assert helpers.l2_rel(helpers.to_np(a.grad), helpers.to_np(b.grad)) <= tol_sh
+        err = helpers.l2_rel(helpers.to_np(a.grad), helpers.to_np(b.grad))
+        if err > tol_sh:
+            bad = ((a.grad - b.grad).reshape(a.shape[0], -1).abs().amax(1) > 1e-6 * float(b.grad.abs().max())).nonzero().view(-1)
+            raise AssertionError("SH leaf %d: l2 %.3e > %.1e; %d rows differ, first %s, union rows among them: %d" % (
+                j, err, tol_sh, bad.numel(), bad[:8].tolist(), int((sb.max_radii[bad] > 0).sum())))
     for i, (a, b) in enumerate(zip(pa.geometry(), pb.geometry())):
-        assert helpers.l2_rel(helpers.to_np(a.grad), helpers.to_np(b.grad)) <= (tol_geo if i == 6 else tol_chain), i
+        err = helpers.l2_rel(helpers.to_np(a.grad), helpers.to_np(b.grad))
+        assert err <= (tol_geo if i == 6 else tol_chain), (i, err)
     assert helpers.l2_rel(helpers.to_np(sa.grad_norm_sum), helpers.to_np(sb.grad_norm_sum)) <= tol_geo
     assert torch.equal(sa.visibility_count.view(-1), sb.visibility_count.view(-1))
     assert torch.equal(sa.max_radii, sb.max_radii)
@@ -130,6 +135,18 @@ def test_factor_mode_equals_dense_backward_one_gpu(name, nviews, split):
     invisible = rs.max_radii <= 0
     assert float(sh_got[invisible].abs().sum()) == 0.0
     assert float(sh_ref.abs().max()) > 0
+
+
+@pytest.mark.parametrize("name,nviews,slots,split", [("small", 1, 2, False), ("mid", 1, 2, True), ("mid", 3, 4, True)])
+def test_factor_mode_with_empty_view_slots(name, nviews, slots, split):
+    """A rank that renders fewer views than the largest shard carries EMPTY view blocks in the factor table (all-zero
+    factors and meta): they must contribute nothing.  world = 1 with views_per_rank > rendered views reproduces that."""
+    cfg, cam, sc, st = helpers.build(name, device=DEV)
+    cams = _views(cfg, nviews, DEV)
+    ref, rs = _sequential(cfg, sc, cams, DEV, split)
+    got, gs, info = _view_parallel(cfg, sc, cams, list(range(nviews)), DEV, split, views_per_rank=slots)
+    assert info["views_total"] == slots
+    _cmp(got, ref, gs, rs, tol_sh=2e-6, tol_geo=1e-4, tol_chain=1e-3 if cfg["P"] < 50000 else 5e-3)
 
 
 def test_sh_outer_sum_kernel_vs_torch_reference():
@@ -217,7 +234,10 @@ def _nccl_worker(rank, world, port, name, nviews, split, out):
         got, gs, info = _view_parallel(cfg, sc, cams, shard_views(nviews, rank, world), dev, split)
         torch.cuda.synchronize(dev)
         # cfg5's long time axis: the reference itself reproduces its chain gradients only to 5-30 % (profiles/)
-        _cmp(got, ref, gs, rs, tol_sh=2e-6, tol_geo=1e-4, tol_chain=1e-3 if cfg["P"] < 50000 else (5e-3 if name != "cfg5" else 2.0))
+        # tol_sh: the factors of the other rank's views carry that rank's blend-backward RED-order noise (~1e-7 per
+        # entry; one of five runs of mid/3 views exceeded 2e-6 on the norm, the other four sat below it) -- a real
+        # exchange error (a missing or misplaced view) is O(1)
+        _cmp(got, ref, gs, rs, tol_sh=1e-5, tol_geo=1e-4, tol_chain=1e-3 if cfg["P"] < 50000 else (5e-3 if name != "cfg5" else 2.0))
         sh = torch.cat([p.grad for p in got.sh_leaves], 1)
         out[rank] = (info, sh.double().sum().item(), sh.cpu() if sc.P <= 20000 else None)
     finally:
