@@ -314,6 +314,19 @@ class ViewParallelStep:
         # at the END of finish() -- the optimistic sparse path is repaired there in the (rare) case it was wrong
         bad = _rows_zero_outside(grads, union) if (grads and world > 1) else torch.zeros(1, dtype=torch.int32, device=union.device)
         bad_work = dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=group, async_op=True) if world > 1 else None
+        bad_host = bad_ready = None
+        if bad_work is not None and bad.is_cuda:
+            # the reduced flag travels to pinned host memory on the side stream as soon as ITS collective is done, so
+            # that reading it at the end of finish() waits for that early event only -- not for the whole step's GPU
+            # work (a full synchronisation there would leave the GPU idle while the host launches the next step)
+            side = _side_stream(bad.device)
+            with torch.cuda.stream(side):
+                bad_work.wait()
+                bad.record_stream(side)
+                bad_host = torch.empty(1, dtype=torch.int32).pin_memory()
+                bad_host.copy_(bad, non_blocking=True)
+                bad_ready = torch.cuda.Event()
+                bad_ready.record(side)
         mask = union > 0
         if union.is_cuda:
             import fdgs
@@ -349,11 +362,22 @@ class ViewParallelStep:
             meta_off = (3 * K + 3) // 4 * 4
             stride = meta_off + 8
             local = torch.zeros(views_per_rank, stride, dtype=torch.float32, device=union.device)
-            for v, rec in enumerate(self.views):
+            if 2 < v_local <= 16 and union.is_cuda:
+                # several local views: ONE row gather for all of them (the pack kernel of the geometry bucket: block v
+                # = view v's K rows, padded to a multiple of 4 floats = meta_off) and three small copies for the
+                # metadata, instead of four launches per view
                 if K > 0:
-                    torch.index_select(rec.factors, 0, idx, out=local[v, :3 * K].view(K, 3))
-                local[v, meta_off] = rec.timestamp
-                local[v, meta_off + 1:meta_off + 4] = rec.campos.reshape(3).to(local.dtype)
+                    flat_f = _pack([rec.factors for rec in self.views], idx)
+                    local[:v_local, :meta_off] = flat_f.view(v_local, meta_off)
+                ts_host = torch.tensor([rec.timestamp for rec in self.views], dtype=torch.float32).pin_memory()
+                local[:v_local, meta_off] = ts_host.to(union.device, non_blocking=True)
+                local[:v_local, meta_off + 1:meta_off + 4] = torch.stack([rec.campos.reshape(3) for rec in self.views]).to(local.dtype)
+            else:
+                for v, rec in enumerate(self.views):
+                    if K > 0:
+                        torch.index_select(rec.factors, 0, idx, out=local[v, :3 * K].view(K, 3))
+                    local[v, meta_off] = rec.timestamp
+                    local[v, meta_off + 1:meta_off + 4] = rec.campos.reshape(3).to(local.dtype)
             self._mark("factor_pack")
         bucket = grads + [st.grad_norm_sum, st.visibility_count]
         flat, geo_works = None, []
@@ -403,8 +427,13 @@ class ViewParallelStep:
         self.views = []
         self._early, self._fwd_radii, self._fwd_count = None, None, 0
         if world > 1:
-            bad_work.wait()
-            if int(bad.item()) != 0 and sparse_ok:
+            if bad_ready is not None:
+                bad_ready.synchronize()
+                is_bad = int(bad_host[0]) != 0
+            else:
+                bad_work.wait()
+                is_bad = int(bad.item()) != 0
+            if is_bad and sparse_ok:
                 # some rank holds gradients outside the union (a loss over ALL Gaussians): the union's rows are summed
                 # already, sum the remaining rows densely
                 self.info["geometry_path"] = "rows + dense repair"
