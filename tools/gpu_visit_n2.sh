@@ -18,3 +18,9 @@ for f in ("bench_n2", "bench_n1"):
     except Exception as e:
         print(f, "FAILED", e); print(open("$OUT/${TAG}_%s.err" % f).read()[-2500:])
 PY
+timeout 300 python bench.py --workload cfg5 --steps 20 --warmup 5 --no-cpu-baseline --no-parity > $OUT/${TAG}_cfg5_n1.json 2> $OUT/${TAG}_cfg5_n1.err
+python - <<PY
+import json
+d = json.loads(open("$OUT/${TAG}_cfg5_n1.json").read().strip().splitlines()[-1])
+print("cfg5 n1", d["value"], d["ms_per_step"], {k: round(v, 4) for k, v in ((d.get("exchange") or {}).get("phase_ms") or {}).items()})
+PY
