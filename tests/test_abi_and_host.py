@@ -96,3 +96,17 @@ def test_means3d_shape_check_raises_before_any_gpu_work():
     with pytest.raises(Exception, match="means3D must have dimensions"):   # reference: rasterize_points.cu:69-71
         C.rasterize_gaussians(torch.zeros(3), bad, e, e, e, e, e, e, e, e, 1.0, e, -1.0, torch.eye(4), torch.eye(4), 1.0,
                               1.0, 16, 16, e, 0, 0, torch.zeros(3), 0.0, 1.0, True, 4, False, False, False)
+
+
+def test_tile_cull_option_round_trip():
+    """fdgs_set_tile_cull is process-wide state of the library: returns the previous mode, defaults to 1 (no GPU needed)."""
+    import fdgs
+    prev = fdgs.set_tile_cull(0)
+    try:
+        assert prev in (0, 1)
+        assert fdgs.set_tile_cull(1) == 0
+        with fdgs.tile_cull(0):
+            assert fdgs.set_tile_cull(0) == 0
+        assert fdgs.set_tile_cull(1) == 1          # the context manager restored mode 1
+    finally:
+        fdgs.set_tile_cull(prev)
