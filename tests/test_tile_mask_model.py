@@ -102,3 +102,39 @@ def test_tile_mask_is_conservative_and_tight():
     # and it is worth something: clearly fewer tiles than the reference's squares, close to what is needed
     assert kept_total < 0.75 * ref_total
     assert kept_total < 1.35 * needed_total + 50
+
+
+def test_tile_mask_extremes():
+    """Large Gaussians (rectangles above 32 tiles: bounding box only), needle-thin ones (axis ratio above ~2000: the
+    reference's rectangle is kept), centres far outside the image, opacity at the 1/255 edge."""
+    rng = np.random.default_rng(11)
+    grid = 12
+    for it in range(600):
+        kind = it % 4
+        if kind == 0:      # huge
+            s1, s2 = np.exp(rng.uniform(np.log(20.0), np.log(200.0), 2))
+        elif kind == 1:    # needle
+            s1, s2 = rng.uniform(40.0, 400.0), rng.uniform(0.01, 0.2)
+        elif kind == 2:    # tiny
+            s1, s2 = rng.uniform(0.05, 0.6, 2)
+        else:
+            s1, s2 = np.exp(rng.uniform(np.log(0.6), np.log(30.0), 2))
+        th = rng.uniform(0, np.pi)
+        R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+        cov = R @ np.diag([s1 * s1, s2 * s2]) @ R.T + 0.3 * np.eye(2)
+        Q = np.linalg.inv(cov)
+        A, B, C = Q[0, 0], Q[0, 1], Q[1, 1]
+        opacity = (1.0 / 255.0) * (1.0 + rng.uniform(0, 0.05)) if it % 7 == 0 else rng.uniform(0.005, 0.99)
+        if opacity < 1.0 / 255.0:
+            continue
+        qc = float(np.log(255.0 * opacity))
+        px, py = rng.uniform(-150, grid * TILE + 150, 2)
+        lam = 0.5 * (cov[0, 0] + cov[1, 1]) + np.sqrt(max(0.1, (0.5 * (cov[0, 0] + cov[1, 1])) ** 2 - np.linalg.det(cov)))
+        rad = int(np.ceil(3.0 * np.sqrt(lam)))
+        clip = lambda v: min(grid, max(0, int(np.floor(v))))
+        rect = (clip((px - rad) / TILE), clip((py - rad) / TILE), clip((px + rad + TILE - 1) / TILE), clip((py + rad + TILE - 1) / TILE))
+        ref_tiles = {(tx, ty) for ty in range(rect[1], rect[3]) for tx in range(rect[0], rect[2])}
+        keep = tile_mask_model(px, py, A, B, C, qc, rect)
+        need = brute_force_tiles(px, py, A, B, C, qc, grid) & ref_tiles
+        assert keep <= ref_tiles
+        assert need <= keep, (it, kind, sorted(need - keep), px, py, A, B, C, qc)
